@@ -1,0 +1,136 @@
+/*
+ * transkun_b200.h -- C ABI of libtranskun_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for Transkun's neural semi-CRF hot path.  The reference has
+ * no native code and therefore no FFI of its own; the
+ * interface each entry point replaces is the Python function it is called from,
+ * cited per function as file:line into /root/reference/transkun/.  The ctypes
+ * binding a maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter is documented as host;
+ *   - score is the reference's [T,T,N] fp32 tensor, contiguous, laid out
+ *     [end][begin][track] (track innermost); noise is [T-1,N] fp32 contiguous;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     every call only enqueues work on it and never synchronises;
+ *   - no allocation happens inside the library: the caller provides outputs and
+ *     workspaces (sizes from the *_bytes functions);
+ *   - return value: 0 on success, a negative TKB_E* code for argument errors,
+ *     a positive cudaError_t for CUDA failures; tkb_last_error() describes the
+ *     last failure of the calling thread.
+ */
+#ifndef TRANSKUN_B200_H
+#define TRANSKUN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TKB_VERSION 1
+
+#define TKB_EINVAL (-1)   /* bad argument (null pointer, T < 1, N < 1, unknown flag) */
+#define TKB_ENODEV (-2)   /* no sm_100 device / kernel image not loadable */
+#define TKB_ELAUNCH (-3)  /* persistent grid does not fit the device */
+
+/* direction of the dynamic programme */
+#define TKB_BACKWARD 0    /* viterbiBackward / beta sweep: positions T-1 .. 0 */
+#define TKB_FORWARD 1     /* viterbi / alpha sweep: positions 0 .. T-1 */
+
+/* which semirings a sweep evaluates (OR them to read the score tensor once) */
+#define TKB_SWEEP_VITERBI 1  /* (max,+): values + back-pointers */
+#define TKB_SWEEP_LOGSUM 2   /* (logsumexp,+): log-partition table */
+
+int tkb_version(void);
+const char *tkb_last_error(void);
+
+/* Device the library would run on is sm_100?  Returns 0 if usable. */
+int tkb_device_check(void);
+
+/*
+ * Workspace for tkb_semicrf_sweep: the inter-CTA mailbox through which solved
+ * table rows are broadcast, plus a status word.  Must be zero-filled once when
+ * allocated; afterwards it is reused across calls, each call passing an `epoch`
+ * strictly greater than any epoch used with this workspace before (re-zero it
+ * if the 32-bit epoch wraps).  One workspace serves one stream at a time.
+ */
+size_t tkb_sweep_workspace_bytes(int T, int N);
+
+/*
+ * The semi-Markov dynamic programme over the lower triangle of score.
+ * Replaces the TorchScript loops of
+ *   CRF/NeuralSemiCRFInterval.py:31-51   viterbiBackward   (BACKWARD | VITERBI)
+ *   CRF/NeuralSemiCRFInterval.py:124-144 viterbi           (FORWARD  | VITERBI)
+ *   CRF/NeuralSemiCRFInterval.py:218-234 computeLogZ       (FORWARD  | LOGSUM)
+ *   CRF/NeuralSemiCRFInterval.py:303-327 beta recursion    (BACKWARD | LOGSUM)
+ * With VITERBI|LOGSUM both tables come out of ONE read of the triangle.
+ *
+ * out_code [N][T] uint32 (track-major), VITERBI only:
+ *     bit 0      = score[t,t,n] > 0 (the singleton (t,t) is emitted when t is visited)
+ *     bits 31..1 = 0 for "skip", else 1 + the chosen partner position
+ *                  (BACKWARD: the end e of interval (t,e); FORWARD: the begin b of (b,t)).
+ *     Ties are resolved exactly as torch.max over the reference's candidate
+ *     list does (skip first, then the first interval candidate).
+ * out_vit  [T][N] fp32 or NULL: the Viterbi table q (BACKWARD) / v (FORWARD),
+ *     bit-identical to the reference's.
+ * out_lse  [T][N] fp32 or NULL: beta (BACKWARD) / alpha (FORWARD), natural log.
+ *     logZ = out_lse[0] (BACKWARD) or out_lse[T-1] (FORWARD).
+ */
+int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
+                      void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit,
+                      float *out_lse, void *stream);
+
+/*
+ * Reads the status word of a sweep workspace (synchronises `stream`).
+ * *status_host (HOST pointer) = 0 if every sweep that used the workspace ran to
+ * completion, non-zero if an inter-CTA wait timed out (results invalid).
+ */
+int tkb_sweep_status(const void *workspace, int *status_host, void *stream);
+
+/*
+ * Back-tracking on the device.  Replaces the per-track host loops
+ *   CRF/NeuralSemiCRFInterval.py:61-102  (BACKWARD; forced_start = begin position, default 0)
+ *   CRF/NeuralSemiCRFInterval.py:157-199 (FORWARD;  forced_start = end position, default T-1)
+ * forced_start: DEVICE int32[N] or NULL for the default.
+ * out_pairs  [N][2*T][2] int32: (begin,end) in the order the reference returns them.
+ * out_counts [N] int32: number of pairs per track.
+ */
+int tkb_semicrf_backtrack(const uint32_t *code, int T, int N, const int32_t *forced_start,
+                          int direction, int32_t *out_pairs, int32_t *out_counts, void *stream);
+
+/*
+ * Marginals (the custom gradient of the log-partition).  Replaces
+ *   CRF/NeuralSemiCRFInterval.py:417-447 (forward_backward) fused with
+ *   CRF/NeuralSemiCRFInterval.py:469-472 (ComputeLogZFasterGrad.backward).
+ * alpha, beta: [T][N] natural-log tables from two LOGSUM sweeps; gscale: [N]
+ * upstream gradient or NULL for 1.  out_grad [T][T][N] dense (zero above the
+ * diagonal), out_grad_noise [T-1][N].
+ */
+int tkb_semicrf_marginals(const float *score, const float *noise, int T, int N, const float *alpha,
+                          const float *beta, const float *gscale, float *out_grad,
+                          float *out_grad_noise, void *stream);
+
+/*
+ * Un-normalised path score.  Replaces CRF/NeuralSemiCRFInterval.py:508-550.
+ * pairs: [total][2] int32 (begin,end), offsets: [N+1] int64 CSR, both DEVICE.
+ * noise_cum: [T][N] workspace (filled with cumsum(pad(noise))), out: [N].
+ */
+int tkb_semicrf_evalpath(const float *score, const float *noise, int T, int N, const int32_t *pairs,
+                         const int64_t *offsets, float *noise_cum, float *out, void *stream);
+
+/*
+ * Gradient of the path score w.r.t. score and noise, ACCUMULATED into dense
+ * buffers (autograd of the gather at :540-548): grad_score[e,b,n] += g[n] per
+ * listed interval; grad_noise[t,n] += g[n] * (1 - #intervals covering [t,t+1]).
+ */
+int tkb_semicrf_evalpath_grad(int T, int N, const int32_t *pairs, const int64_t *offsets,
+                              const float *gscale, float sign, float *grad_score, float *grad_noise,
+                              void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSKUN_B200_H */

@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's golden outputs and
+the CPU oracle.  Decode and the Viterbi table are bit-exact; log-partition / path scores /
+marginals within the north star's 1e-4 relative tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, golden_cases, make_inputs, random_intervals
+from oracle.semicrf_oracle import SemiCRFOracle
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4  # BASELINE.json north_star: logProb within 1e-4 relative
+CASES = golden_cases()
+
+
+def _ids(paths):
+    return [p.split("/")[-1][:-4] for p in paths]
+
+
+def _crf(score, noise, requires_grad=False):
+    from transkun_b200.CRF import NeuralSemiCRFInterval
+    s = torch.from_numpy(score).cuda()
+    z = torch.from_numpy(noise).cuda()
+    if requires_grad:
+        s.requires_grad_()
+        z.requires_grad_()
+    return NeuralSemiCRFInterval(s, z), s, z
+
+
+@pytest.mark.parametrize("path", CASES, ids=_ids(CASES))
+def test_golden(path):
+    g = Golden(path)
+    inp = g.inputs()
+    if inp is None:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    crf, _, _ = _crf(*inp)
+    with torch.no_grad():
+        assert crf.decode() == g.lists("dec_bwd")
+        assert crf.decode(forward=True) == g.lists("dec_fwd")
+        assert crf.decode(forcedStartPos=g["forced_bwd"].tolist()) == g.lists("dec_bwd_forced")
+        assert crf.decode(forcedStartPos=g["forced_fwd"].tolist(), forward=True) == g.lists("dec_fwd_forced")
+        np.testing.assert_allclose(crf.computeLogZ(noBackward=True).cpu().numpy(), g["logz_fwd"], rtol=RTOL)
+        dec, logz_b = crf.decodeWithLogZ()
+        assert dec == g.lists("dec_bwd")
+        np.testing.assert_allclose(logz_b.cpu().numpy(), g["logz_fwd"], rtol=RTOL)
+        iv = g.lists("iv")
+        np.testing.assert_allclose(crf.evalPath(iv).cpu().numpy(), g["evalpath"], rtol=RTOL, atol=1e-4)
+        np.testing.assert_allclose(crf.logProb(iv).cpu().numpy(), g["logprob"], rtol=RTOL, atol=1e-3)
+
+
+@pytest.mark.parametrize("path", [p for p in CASES if Golden(p).has("grad")], ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_gradients(path):
+    g = Golden(path)
+    crf, s, z = _crf(*g.inputs(), requires_grad=True)
+    logz = crf.computeLogZ()
+    np.testing.assert_allclose(logz.detach().cpu().numpy(), g["logz_fb"], rtol=RTOL)
+    logz.sum().backward()
+    np.testing.assert_allclose(s.grad.cpu().numpy(), g["grad"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(z.grad.cpu().numpy(), g["grad_noise"], rtol=1e-3, atol=1e-6)
+    assert torch.all(s.grad[torch.triu_indices(g.T, g.T, 1).unbind()[0], torch.triu_indices(g.T, g.T, 1).unbind()[1]] == 0)
+
+
+@pytest.mark.parametrize("T,N,kind", [(1, 3, "randn"), (2, 1, "randn"), (31, 7, "randn"), (32, 8, "ties"),
+                                      (33, 9, "ties"), (63, 4, "model"), (64, 90, "randn"), (65, 17, "ties"),
+                                      (96, 360, "randn"), (129, 88, "model"), (257, 24, "ties"), (8, 1200, "randn")])
+def test_against_oracle_tables(T, N, kind):
+    """Viterbi table bit-exact, back-pointers identical, log tables within tolerance, both directions."""
+    from transkun_b200.CRF.NeuralSemiCRFInterval import sweep
+    from transkun_b200._lib import BACKWARD, FORWARD, SWEEP_LOGSUM, SWEEP_VITERBI
+    if T == 1:
+        score = np.random.RandomState(0).randn(1, 1, N).astype(np.float32)
+        noise = np.zeros((0, N), dtype=np.float32)
+    else:
+        score, noise = make_inputs(kind, T, N, 7)
+    o = SemiCRFOracle(score, noise)
+    s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
+    for direction, forward in ((BACKWARD, False), (FORWARD, True)):
+        code, vit, lse, _ = sweep(s, z, direction, SWEEP_VITERBI | SWEEP_LOGSUM, want_vit=True)
+        q, sel = o.viterbi_dp(forward)
+        assert np.array_equal(vit.cpu().numpy().view(np.uint32), q.view(np.uint32)), "Viterbi table not bit-exact"
+        code = code.cpu().numpy().view(np.uint32).T  # [T, N]
+        assert np.array_equal((code >> 1).astype(np.int64) - 1, sel.astype(np.int64))
+        diag = np.stack([np.diag(score[:, :, n]) for n in range(N)], -1) > 0
+        assert np.array_equal((code & 1).astype(bool), diag)
+        ref = o.alpha() if forward else o.beta()
+        np.testing.assert_allclose(lse.cpu().numpy(), ref, rtol=RTOL, atol=1e-4)
+        # single-semiring launches give the same tables
+        code1, vit1, _, _ = sweep(s, z, direction, SWEEP_VITERBI, want_vit=True)
+        assert torch.equal(vit1, vit)
+        _, _, lse1, _ = sweep(s, z, direction, SWEEP_LOGSUM)
+        assert torch.equal(lse1, lse)
+    if T > 1:
+        from transkun_b200.CRF import NeuralSemiCRFInterval
+        crf = NeuralSemiCRFInterval(s, z)
+        rs = np.random.RandomState(T + N)
+        f1, f2 = rs.randint(0, T, size=N).tolist(), rs.randint(0, T, size=N).tolist()
+        assert crf.decode() == o.decode()
+        assert crf.decode(forward=True) == o.decode(forward=True)
+        assert crf.decode(forcedStartPos=f1) == o.decode(forcedStartPos=f1)
+        assert crf.decode(forcedStartPos=f2, forward=True) == o.decode(forcedStartPos=f2, forward=True)
+
+
+@pytest.mark.parametrize("T", [1024, 2048])
+def test_full_size_parity_and_properties(T):
+    """BASELINE.json configs[1] and the metric's T=2048, N=88: full comparison against the oracle
+    (the C oracle finishes in about a second) plus size-independent properties."""
+    N = 88
+    score, noise = make_inputs("randn", T, N, 1234)
+    o = SemiCRFOracle(score, noise)
+    crf, s, z = _crf(score, noise)
+    with torch.no_grad():
+        dec, logz = crf.decodeWithLogZ()
+        assert dec == o.decode()
+        ref_logz = o.computeLogZ()
+        np.testing.assert_allclose(logz.cpu().numpy(), ref_logz, rtol=RTOL)
+        np.testing.assert_allclose(crf.computeLogZ(noBackward=True).cpu().numpy(), ref_logz, rtol=RTOL)
+        # properties: the decoded path's score equals the Viterbi value and is below logZ
+        best = crf.evalPath(dec).cpu().numpy()
+        q, _ = o.viterbi_dp(False)
+        np.testing.assert_allclose(best, q[0], rtol=1e-5)
+        assert np.all(logz.cpu().numpy() >= best)
+        # idempotence / determinism: same bits on a second run
+        dec2, logz2 = crf.decodeWithLogZ()
+        assert dec2 == dec and torch.equal(logz2, logz)
+        # forced start = suffix property: decoding from position p reproduces the tail of a path through p
+        p = dec[0][len(dec[0]) // 2][0]
+        tail = crf.decode(forcedStartPos=[p] * N)[0]
+        assert tail == [iv for iv in dec[0] if iv[0] >= p]
+
+
+def test_logprob_autograd_matches_oracle():
+    T, N = 48, 10
+    score, noise = make_inputs("randn", T, N, 3)
+    o = SemiCRFOracle(score, noise)
+    iv = random_intervals(T, N, 11)
+    crf, s, z = _crf(score, noise, requires_grad=True)
+    w = torch.linspace(0.5, 1.5, N, device="cuda")
+    lp = crf.logProb(iv)
+    np.testing.assert_allclose(lp.detach().cpu().numpy(), o.logProb(iv), rtol=RTOL, atol=1e-3)
+    (lp * w).sum().backward()
+    _, grad, gn = o.marginals()
+    onehot = np.zeros_like(grad)
+    cover = np.zeros_like(gn)
+    for n, cur in enumerate(iv):
+        for b, e in cur:
+            onehot[e, b, n] += 1
+            cover[b:e, n] += 1
+    wn = w.cpu().numpy()
+    np.testing.assert_allclose(s.grad.cpu().numpy(), (onehot - grad) * wn, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(z.grad.cpu().numpy(), ((1 - cover) - gn) * wn, rtol=1e-3, atol=1e-5)
+    # the separate ops compose to the same gradient
+    crf2, s2, z2 = _crf(score, noise, requires_grad=True)
+    ((crf2.evalPath(iv) - crf2.computeLogZ()) * w).sum().backward()
+    np.testing.assert_allclose(s2.grad.cpu().numpy(), s.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(z2.grad.cpu().numpy(), z.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_fit_demo_converges():
+    """The reference's only behavioural check (:591-622): Adam on score/noise until decode() returns the targets."""
+    from transkun_b200.CRF import NeuralSemiCRFInterval
+    torch.manual_seed(0)
+    score = torch.randn(40, 40, 4).cuda().requires_grad_()
+    noise = torch.randn(39, 4).cuda().requires_grad_()
+    intervals = [[(0, 2), (4, 6), (6, 6), (7, 8)], [(1, 2), (3, 5), (19, 19)], [(0, 0), (4, 7)], []]
+    opt = torch.optim.Adam([score, noise], 5e-2)
+    for _ in range(400):
+        opt.zero_grad()
+        crf = NeuralSemiCRFInterval(score, noise)
+        loss = -(crf.evalPath(intervals) - crf.computeLogZ()).sum()
+        loss.backward()
+        opt.step()
+    with torch.no_grad():
+        assert NeuralSemiCRFInterval(score, noise).decode() == intervals
+    assert float(loss) < 1.0

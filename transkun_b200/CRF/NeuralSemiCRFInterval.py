@@ -1,0 +1,363 @@
+"""The neural semi-CRF output layer, B200-native.
+
+Drop-in for the reference class `NeuralSemiCRFInterval`
+(/root/reference/transkun/CRF/NeuralSemiCRFInterval.py:553-588): same
+constructor, same four methods, same return types.  All arithmetic runs in
+hand-written sm_100a CUDA (libtranskun_b200.so, include/transkun_b200.h); this
+file only validates arguments, allocates outputs/workspaces with torch and turns
+packed device results into the Python objects the reference returns.  There is
+no CPU path: tensors must live on a CUDA device.
+
+    score      [T, T, N] : score of every closed interval [begin, end], laid out
+                           [end, begin, track]; only end >= begin is read
+    noiseScore [T-1, N]  : score of "no event between t and t+1"
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import BACKWARD, FORWARD, SWEEP_LOGSUM, SWEEP_VITERBI
+
+Intervals = List[List[Tuple[int, int]]]
+
+
+# ---------------------------------------------------------------------------
+# plumbing
+# ---------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Workspace:
+    """Mailbox of the persistent sweep kernel: zero-filled once, then reused with a growing epoch."""
+
+    def __init__(self, T: int, N: int, device: torch.device):
+        nbytes = _lib.load().tkb_sweep_workspace_bytes(T, N)
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.epoch = 0
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        if self.epoch >= 0xFFFFFFFF:
+            self.buf.zero_()
+            self.epoch = 1
+        return self.epoch
+
+
+_workspaces: Dict[tuple, _Workspace] = {}
+
+
+def _workspace(T: int, N: int, device: torch.device, slot: int = 0) -> _Workspace:
+    key = (device.index, _stream(device), T, N, slot)
+    ws = _workspaces.get(key)
+    if ws is None:
+        if len(_workspaces) > 64:
+            _workspaces.clear()
+        ws = _workspaces[key] = _Workspace(T, N, device)
+    return ws
+
+
+def _check_inputs(score: torch.Tensor, noiseScore: torch.Tensor):
+    # the reference asserts these in TorchScript (:17-18, :111-112, :209-215, :377-382)
+    assert score.dim() == 3, "score must be [T, T, nBatch]"
+    assert score.shape[0] == score.shape[1], "score must be square in its first two dims"
+    T, N = score.shape[0], score.shape[2]
+    assert noiseScore.dim() == 2 and noiseScore.shape[0] == T - 1 and noiseScore.shape[1] == N, \
+        "noiseScore must be [T-1, nBatch]"
+    if not score.is_cuda or not noiseScore.is_cuda:
+        raise RuntimeError("transkun_b200 has no CPU path: score/noiseScore must be CUDA tensors")
+    if score.device != noiseScore.device:
+        raise RuntimeError("score and noiseScore must be on the same device")
+    return T, N
+
+
+def _prep(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()  # the reference's DP tables are fp32 regardless of the input dtype (:22, :116)
+    return t.contiguous()
+
+
+def sweep(score: torch.Tensor, noise: torch.Tensor, direction: int, flags: int, want_vit: bool = False,
+          slot: int = 0):
+    """One pass of the persistent DP kernel.  Returns (code[N,T] int32 | None, vit[T,N] | None, lse[T,N] | None)."""
+    T, N = score.shape[0], score.shape[2]
+    dev = score.device
+    L = _lib.load()
+    ws = _workspace(T, N, dev, slot)
+    code = torch.empty((N, T), dtype=torch.int32, device=dev) if flags & SWEEP_VITERBI else None
+    vit = torch.empty((T, N), dtype=torch.float32, device=dev) if (flags & SWEEP_VITERBI and want_vit) else None
+    lse = torch.empty((T, N), dtype=torch.float32, device=dev) if flags & SWEEP_LOGSUM else None
+    with torch.cuda.device(dev):
+        rc = L.tkb_semicrf_sweep(_ptr(score), _ptr(noise) if T > 1 else None, T, N, direction, flags,
+                                 _ptr(ws.buf), ws.next_epoch(), _ptr(code), _ptr(vit), _ptr(lse), _stream(dev))
+    _lib.check(rc, "tkb_semicrf_sweep")
+    return code, vit, lse, ws
+
+
+def backtrack(code: torch.Tensor, forced: Optional[torch.Tensor], direction: int):
+    N, T = code.shape
+    dev = code.device
+    pairs = torch.empty((N, 2 * T, 2), dtype=torch.int32, device=dev)
+    counts = torch.empty((N,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tkb_semicrf_backtrack(_ptr(code), T, N, _ptr(forced), direction, _ptr(pairs), _ptr(counts),
+                                               _stream(dev))
+    _lib.check(rc, "tkb_semicrf_backtrack")
+    return pairs, counts
+
+
+def _forced_tensor(forcedStartPos: Optional[Sequence[int]], N: int, T: int, dev) -> Optional[torch.Tensor]:
+    if forcedStartPos is None:
+        return None
+    if torch.is_tensor(forcedStartPos):
+        f = forcedStartPos.to(device=dev, dtype=torch.int32)
+    else:
+        f = np.asarray(list(forcedStartPos), dtype=np.int64)
+        if f.shape != (N,):
+            raise ValueError(f"forcedStartPos must have one entry per track ({N}), got shape {f.shape}")
+        if (f < 0).any():
+            raise IndexError("forcedStartPos must be >= 0")
+        f = torch.from_numpy(np.minimum(f, T - 1).astype(np.int32)).to(dev, non_blocking=True)
+    assert f.shape == (N,)
+    return f.contiguous()
+
+
+def _csr(intervals: Intervals, N: int, T: int, dev):
+    if len(intervals) != N:
+        raise ValueError(f"intervals must have one list per track ({N}), got {len(intervals)}")
+    lens = np.fromiter((len(c) for c in intervals), dtype=np.int64, count=N)
+    offsets = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    flat = np.asarray([p for cur in intervals for p in cur], dtype=np.int32).reshape(-1, 2)
+    if flat.size and (flat.min() < 0 or flat.max() >= T):
+        raise IndexError("interval endpoints must lie in [0, T)")
+    pairs = torch.from_numpy(np.ascontiguousarray(flat)).to(dev, non_blocking=True)
+    if pairs.numel() == 0:
+        pairs = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    return pairs, torch.from_numpy(offsets).to(dev, non_blocking=True)
+
+
+def _pairs_to_lists(pairs: torch.Tensor, counts: torch.Tensor) -> Intervals:
+    counts_h = counts.cpu()  # synchronises (the reference synchronises at ptr.cpu(), :56)
+    maxc = int(counts_h.max()) if counts_h.numel() else 0
+    pairs_h = pairs[:, :maxc].cpu().numpy() if maxc > 0 else np.zeros((pairs.shape[0], 0, 2), dtype=np.int32)
+    out: Intervals = []
+    for n, c in enumerate(counts_h.tolist()):
+        out.append(list(map(tuple, pairs_h[n, :c].tolist())))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# autograd
+# ---------------------------------------------------------------------------
+def _alpha_beta(score: torch.Tensor, noise: torch.Tensor):
+    """alpha (forward) and beta (backward) log-sum tables; two independent sweeps."""
+    _, _, alpha, _ = sweep(score, noise, FORWARD, SWEEP_LOGSUM, slot=1)
+    _, _, beta, _ = sweep(score, noise, BACKWARD, SWEEP_LOGSUM, slot=0)
+    return alpha, beta
+
+
+def _marginals(score, noise, alpha, beta, gscale, want_score: bool, want_noise: bool):
+    T, N = score.shape[0], score.shape[2]
+    dev = score.device
+    grad = torch.empty_like(score) if want_score else None
+    gnoise = torch.empty_like(noise) if (want_noise and T > 1) else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().tkb_semicrf_marginals(_ptr(score), _ptr(noise) if T > 1 else None, T, N, _ptr(alpha),
+                                               _ptr(beta), _ptr(gscale), _ptr(grad), _ptr(gnoise), _stream(dev))
+    _lib.check(rc, "tkb_semicrf_marginals")
+    if want_noise and gnoise is None:
+        gnoise = torch.zeros_like(noise)
+    return grad, gnoise
+
+
+class _LogZFn(torch.autograd.Function):
+    """log Z with the closed-form marginal gradient (reference ComputeLogZFasterGrad, :459-475).
+
+    Unlike the reference, the dense [T,T,N] gradient is not materialised in forward and
+    kept alive; forward keeps only alpha/beta ([T,N] each) and backward writes
+    grad * grad_output in a single pass over the triangle."""
+
+    @staticmethod
+    def forward(ctx, score, noiseScore):
+        s, z = _prep(score), _prep(noiseScore)
+        alpha, beta = _alpha_beta(s, z)
+        ctx.save_for_backward(s, z, alpha, beta)
+        ctx.in_dtypes = (score.dtype, noiseScore.dtype)
+        return alpha[-1].clone()  # logZ = v[-1] (:417)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        s, z, alpha, beta = ctx.saved_tensors
+        g = grad_output.detach().to(torch.float32).contiguous()
+        assert g.shape[-1] == s.shape[-1]  # (:471)
+        grad, gnoise = _marginals(s, z, alpha, beta, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        if grad is not None and ctx.in_dtypes[0] != torch.float32:
+            grad = grad.to(ctx.in_dtypes[0])
+        if gnoise is not None and ctx.in_dtypes[1] != torch.float32:
+            gnoise = gnoise.to(ctx.in_dtypes[1])
+        return grad, gnoise
+
+
+def _evalpath_forward(s, z, pairs, offsets):
+    T, N = s.shape[0], s.shape[2]
+    dev = s.device
+    cum = torch.empty((T, N), dtype=torch.float32, device=dev)
+    out = torch.empty((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tkb_semicrf_evalpath(_ptr(s), _ptr(z) if T > 1 else None, T, N, _ptr(pairs), _ptr(offsets),
+                                              _ptr(cum), _ptr(out), _stream(dev))
+    _lib.check(rc, "tkb_semicrf_evalpath")
+    return out
+
+
+def _evalpath_backward_into(T, N, pairs, offsets, g, sign, grad, gnoise, dev):
+    with torch.cuda.device(dev):
+        rc = _lib.load().tkb_semicrf_evalpath_grad(T, N, _ptr(pairs), _ptr(offsets), _ptr(g), float(sign), _ptr(grad),
+                                                   _ptr(gnoise), _stream(dev))
+    _lib.check(rc, "tkb_semicrf_evalpath_grad")
+
+
+class _EvalPathFn(torch.autograd.Function):
+    """Un-normalised path score (reference evalPath, :508-550); gradient = the gather's adjoint."""
+
+    @staticmethod
+    def forward(ctx, score, noiseScore, pairs, offsets):
+        s, z = _prep(score), _prep(noiseScore)
+        ctx.save_for_backward(pairs, offsets)
+        ctx.shape = (s.shape[0], s.shape[2])
+        ctx.in_dtypes = (score.dtype, noiseScore.dtype)
+        return _evalpath_forward(s, z, pairs, offsets)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        pairs, offsets = ctx.saved_tensors
+        T, N = ctx.shape
+        dev = grad_output.device
+        g = grad_output.detach().to(torch.float32).contiguous()
+        grad = torch.zeros((T, T, N), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        gnoise = torch.zeros((max(T - 1, 0), N), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        _evalpath_backward_into(T, N, pairs, offsets, g, 1.0, grad, gnoise, dev)
+        if grad is not None:
+            grad = grad.to(ctx.in_dtypes[0])
+        if gnoise is not None:
+            gnoise = gnoise.to(ctx.in_dtypes[1])
+        return grad, gnoise, None, None
+
+
+class _LogProbFn(torch.autograd.Function):
+    """evalPath - logZ with ONE dense gradient buffer: path indicators minus marginals."""
+
+    @staticmethod
+    def forward(ctx, score, noiseScore, pairs, offsets):
+        s, z = _prep(score), _prep(noiseScore)
+        alpha, beta = _alpha_beta(s, z)
+        path = _evalpath_forward(s, z, pairs, offsets)
+        ctx.save_for_backward(s, z, alpha, beta, pairs, offsets)
+        ctx.in_dtypes = (score.dtype, noiseScore.dtype)
+        return path - alpha[-1]
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        s, z, alpha, beta, pairs, offsets = ctx.saved_tensors
+        T, N = s.shape[0], s.shape[2]
+        g = grad_output.detach().to(torch.float32).contiguous()
+        grad, gnoise = _marginals(s, z, alpha, beta, -g, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        _evalpath_backward_into(T, N, pairs, offsets, g, 1.0, grad, gnoise, s.device)
+        if grad is not None:
+            grad = grad.to(ctx.in_dtypes[0])
+        if gnoise is not None:
+            gnoise = gnoise.to(ctx.in_dtypes[1])
+        return grad, gnoise, None, None
+
+
+# ---------------------------------------------------------------------------
+# the reference's class
+# ---------------------------------------------------------------------------
+class NeuralSemiCRFInterval:
+    def __init__(self, score, noiseScore):
+        """The output layer for multiple tracks of non-overlapping intervals
+
+        arguments:
+        score -- the score matrix for all possible [begin, end] pairs, shape [T, T, nBatch]
+        noiseScore -- the non-event score for the interval [t, t+1], shape [T-1, nBatch]
+        (reference :554-564; the object only borrows the two tensors)
+        """
+        self.score = score
+        self.noiseScore = noiseScore
+
+    # -- packed device-side results (what a fused caller should use) -----------------------
+    def decode_packed(self, forcedStartPos=None, forward: bool = False, with_logz: bool = False):
+        """Viterbi on the device.  Returns (pairs[N, 2T, 2] int32, counts[N] int32, logZ[N] | None), all on
+        score.device, nothing synchronised.  with_logz=True also evaluates the log-partition in the SAME
+        pass over the score tensor (BACKWARD direction only, where both tables walk the triangle alike)."""
+        T, N = _check_inputs(self.score, self.noiseScore)
+        s, z = _prep(self.score), _prep(self.noiseScore)
+        direction = FORWARD if forward else BACKWARD
+        flags = SWEEP_VITERBI | (SWEEP_LOGSUM if with_logz else 0)
+        code, _, lse, ws = sweep(s, z, direction, flags)
+        forced = _forced_tensor(forcedStartPos, N, T, s.device)
+        pairs, counts = backtrack(code, forced, direction)
+        logz = None
+        if with_logz:
+            logz = lse[T - 1 if forward else 0].clone()
+        self._last_ws = ws
+        return pairs, counts, logz
+
+    def _raise_if_timed_out(self):
+        ws = getattr(self, "_last_ws", None)
+        if ws is not None and int(ws.buf[:4].view(torch.int32).item()) != 0:
+            raise _lib.TkbError("semi-CRF sweep: an inter-CTA wait timed out; results are invalid")
+
+    # -- reference surface -------------------------------------------------------------------
+    def decode(self, forcedStartPos=None, forward=False) -> Intervals:
+        """Viterbi decoding (reference :567-571 -> viterbi :107 / viterbiBackward :13)."""
+        pairs, counts, _ = self.decode_packed(forcedStartPos, forward)
+        out = _pairs_to_lists(pairs, counts)
+        self._raise_if_timed_out()
+        return out
+
+    def decodeWithLogZ(self, forcedStartPos=None):
+        """decode() and computeLogZ(noBackward=True) from one read of the score tensor."""
+        pairs, counts, logz = self.decode_packed(forcedStartPos, False, with_logz=True)
+        out = _pairs_to_lists(pairs, counts)
+        self._raise_if_timed_out()
+        return out, logz
+
+    def evalPath(self, intervals: Intervals):
+        """compute the unnormalized score (reference :574-577)"""
+        T, N = _check_inputs(self.score, self.noiseScore)
+        pairs, offsets = _csr(intervals, N, T, self.score.device)
+        return _EvalPathFn.apply(self.score, self.noiseScore, pairs, offsets)
+
+    def computeLogZ(self, noBackward=False):
+        """compute the log normalization factor (reference :580-585)"""
+        T, N = _check_inputs(self.score, self.noiseScore)
+        needs_grad = torch.is_grad_enabled() and (self.score.requires_grad or self.noiseScore.requires_grad)
+        if needs_grad:
+            # noBackward=True differentiates the same value through autograd in the reference (:583);
+            # the closed-form marginals are that gradient
+            return _LogZFn.apply(self.score, self.noiseScore)
+        s, z = _prep(self.score), _prep(self.noiseScore)
+        _, _, alpha, _ = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
+        return alpha[-1].clone()
+
+    def logProb(self, intervals: Intervals, noBackward=False):
+        """evalPath - computeLogZ (reference :587-588)"""
+        T, N = _check_inputs(self.score, self.noiseScore)
+        pairs, offsets = _csr(intervals, N, T, self.score.device)
+        needs_grad = torch.is_grad_enabled() and (self.score.requires_grad or self.noiseScore.requires_grad)
+        if needs_grad:
+            return _LogProbFn.apply(self.score, self.noiseScore, pairs, offsets)
+        s, z = _prep(self.score), _prep(self.noiseScore)
+        _, _, alpha, _ = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
+        return _evalpath_forward(s, z, pairs, offsets) - alpha[-1]

@@ -1,0 +1,70 @@
+"""ctypes binding of libtranskun_b200.so (include/transkun_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing this module
+raises, and every entry point raises on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libtranskun_b200.so")
+_lib = None
+
+BACKWARD, FORWARD = 0, 1
+SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
+
+# every symbol include/transkun_b200.h declares
+EXPORTS = (
+    "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
+    "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
+    "tkb_semicrf_evalpath_grad",
+)
+
+
+class TkbError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise TkbError(
+            f"{_LIB_PATH} is missing: build it with `python -m transkun_b200.build` "
+            "(nvcc, sm_100a). transkun_b200 has no CPU or PyTorch fallback.")
+    import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library needs it)
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, i, u32, sz, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_float
+    L.tkb_version.restype = i
+    L.tkb_last_error.restype = ctypes.c_char_p
+    L.tkb_device_check.restype = i
+    L.tkb_sweep_workspace_bytes.restype = sz
+    L.tkb_sweep_workspace_bytes.argtypes = [i, i]
+    L.tkb_semicrf_sweep.restype = i
+    L.tkb_semicrf_sweep.argtypes = [vp, vp, i, i, i, i, vp, u32, vp, vp, vp, vp]
+    L.tkb_sweep_status.restype = i
+    L.tkb_sweep_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int), vp]
+    L.tkb_semicrf_backtrack.restype = i
+    L.tkb_semicrf_backtrack.argtypes = [vp, i, i, vp, i, vp, vp, vp]
+    L.tkb_semicrf_marginals.restype = i
+    L.tkb_semicrf_marginals.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp]
+    L.tkb_semicrf_evalpath.restype = i
+    L.tkb_semicrf_evalpath.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp]
+    L.tkb_semicrf_evalpath_grad.restype = i
+    L.tkb_semicrf_evalpath_grad.argtypes = [i, i, vp, vp, vp, f, vp, vp, vp]
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tkb_last_error().decode("utf-8", "replace")
+        raise TkbError(f"{what} failed with status {rc}: {msg}")
