@@ -1,0 +1,67 @@
+"""Track sharding across the GPUs of one box.
+
+The CRF instances (tracks, the innermost axis of score[T,T,N]) are independent,
+so the path shards with NO data-path collective: rank r owns a contiguous slice
+of tracks and runs the whole sweep + backtrack locally.  The only exchange is the
+gather of the packed decoded intervals (and the [N] log-partitions), one NCCL
+all-gather of fixed-size records over NVLink; message sizes are latency-bound.
+
+Shard upstream: a slice of an existing dense [T,T,N] tensor along its innermost
+axis is strided, so each rank should produce (scorer) or receive its own
+contiguous [T,T,N_r] block.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def track_shard(n_tracks: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of the track axis owned by `rank` (first ranks get the remainder)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n_tracks, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_tracks: int, world: int) -> List[int]:
+    return [track_shard(n_tracks, world, r)[1] - track_shard(n_tracks, world, r)[0] for r in range(world)]
+
+
+def gather_decoded(pairs: torch.Tensor, counts: torch.Tensor, n_tracks: int, max_pairs: Optional[int] = None,
+                   group=None):
+    """All-gather packed decode results of a track-sharded problem.
+
+    pairs [n_local, P, 2] int32, counts [n_local] int32 on every rank (n_local may differ by one between
+    ranks).  Returns (pairs [n_tracks, P', 2], counts [n_tracks]) identical on every rank, tracks in global
+    order.  P' = max_pairs (records are truncated to it before the exchange) or P.
+    """
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_tracks, world)
+    nmax = max(sizes)
+    P = pairs.shape[1] if max_pairs is None else min(max_pairs, pairs.shape[1])
+    rec = torch.zeros((nmax, P * 2 + 1), dtype=torch.int32, device=pairs.device)  # fixed-size padded records
+    n_local = pairs.shape[0]
+    rec[:n_local, 0] = counts
+    rec[:n_local, 1:] = pairs[:, :P].reshape(n_local, P * 2)
+    out = torch.empty((world * nmax, P * 2 + 1), dtype=torch.int32, device=pairs.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    out = out.view(world, nmax, P * 2 + 1)
+    keep = torch.cat([out[r, :sizes[r]] for r in range(world)], 0)
+    return keep[:, 1:].reshape(n_tracks, P, 2), keep[:, 0].contiguous()
+
+
+def gather_vector(v: torch.Tensor, n_tracks: int, group=None) -> torch.Tensor:
+    """All-gather a per-track vector ([n_local] -> [n_tracks]), e.g. log-partitions or log-probabilities."""
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_tracks, world)
+    nmax = max(sizes)
+    buf = torch.zeros((nmax,), dtype=v.dtype, device=v.device)
+    buf[: v.shape[0]] = v
+    out = torch.empty((world * nmax,), dtype=v.dtype, device=v.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.view(world, nmax)
+    return torch.cat([out[r, :sizes[r]] for r in range(world)], 0)
