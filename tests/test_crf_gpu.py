@@ -88,7 +88,8 @@ def test_against_oracle_tables(T, N, kind):
         code1, vit1, _, _ = sweep(s, z, direction, SWEEP_VITERBI, want_vit=True)
         assert torch.equal(vit1, vit)
         _, _, lse1, _ = sweep(s, z, direction, SWEEP_LOGSUM)
-        assert torch.equal(lse1, lse)
+        # (the fused and the single-semiring instantiations may contract FMAs differently)
+        np.testing.assert_allclose(lse1.cpu().numpy(), lse.cpu().numpy(), rtol=1e-5, atol=1e-5)
     if T > 1:
         from transkun_b200.CRF import NeuralSemiCRFInterval
         crf = NeuralSemiCRFInterval(s, z)

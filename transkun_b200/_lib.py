@@ -8,7 +8,9 @@ from __future__ import annotations
 import ctypes
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libtranskun_b200.so")
+# TKB_LIBRARY selects an alternative build of the SAME sources (e.g. the -DTKB_TIMELINE diagnostics build)
+_LIB_PATH = os.environ.get("TKB_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
+                                                          "libtranskun_b200.so")
 _lib = None
 
 BACKWARD, FORWARD = 0, 1

@@ -32,11 +32,11 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    if not force and out == LIB and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB, *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-o", out, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -45,7 +45,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
+
+
+def build_timeline() -> str:
+    """Diagnostics build: same sources with -DTKB_TIMELINE (per-block globaltimer stamps)."""
+    return build(force=True, defines=("TKB_TIMELINE",), out=os.path.join(CSRC, "libtranskun_b200_timeline.so"))
 
 
 if __name__ == "__main__":

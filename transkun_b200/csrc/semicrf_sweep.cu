@@ -36,13 +36,18 @@ constexpr int NG = 8;      // tracks per group
 constexpr int BX = 32;     // columns per block (= lanes of a solver warp)
 constexpr int NW = 16;     // warps per CTA: far field 16 row-slices; solve 8 tracks x 2 semirings
 constexpr int NT = NW * 32;
-constexpr int SLOTS = 6;   // per-warp FIFO depth (rows); SLOTS-1 rows in flight
+constexpr int SLOTS = 8;   // per-warp FIFO depth (rows); SLOTS-1 rows in flight
 constexpr int CH = 4;      // rows per log-sum-exp rescale chunk
 
-constexpr size_t kRingFloats = (size_t)NW * SLOTS * 2 * 32 * 4;
-constexpr size_t kMergeEntries = (size_t)NW * NG * BX;  // float2 each, one array per semiring
+// shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) | diagonal block.
+// After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
+// solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
+constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 32 * 4;
+constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 16;
 constexpr size_t kDiagFloats = (size_t)NG * BX * BX;
-constexpr size_t kSweepSmem = kRingFloats * 4 + 2 * kMergeEntries * 8 + kDiagFloats * 4;
+constexpr size_t kSweepSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + kDiagFloats * 4;
+static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
 
@@ -57,6 +62,7 @@ struct SweepParams {
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
     float *outl;     // [T][N] or null
+    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][4] globaltimer stamps
 };
 
 // Wait until the mailbox word carries this launch's epoch.  A protocol bug (or a
@@ -85,16 +91,28 @@ __device__ __forceinline__ void publish(unsigned long long *w, float val, unsign
     st_relaxed_u64(w, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val));
 }
 
+#ifdef TKB_TIMELINE
+#define TKB_STAMP(slot)                                                                                   \
+    do {                                                                                                  \
+        if (threadIdx.x == 0 && p.timeline && owned_idx < 64)                                             \
+            p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * 4 + (slot)] = globaltimer_ns();            \
+    } while (0)
+#else
+#define TKB_STAMP(slot) \
+    do {                \
+    } while (0)
+#endif
+
 template <int DIR, bool A16, int MODE>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
     constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
+    constexpr int D = SLOTS - 1;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
-    float2 *mergeV = reinterpret_cast<float2 *>(ring + kRingFloats);
-    float2 *mergeL = mergeV + kMergeEntries;
-    float *diagS = reinterpret_cast<float *>(mergeL + kMergeEntries);  // [NG][BX rows][BX cols]
+    unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
+    float *diagS = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);  // [NG][BX rows][BX cols]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -109,15 +127,25 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int cpair = lane >> 1, quad = lane & 1;
     const int nq = n0 + quad * 4;
     const int nvalid = min(max(N - nq, 0), 4);
-    float *my_ring = ring + ((size_t)warp * SLOTS * 2 * 32 + lane) * 4;  // + (slot*2+piece)*128 floats
+    float *my_ring = ring + (size_t)warp * kRingFloatsPerWarp + lane * 4;  // + slot*256 (+128 for column 1)
+    unsigned long long *my_q = qring + (size_t)warp * kQWordsPerWarp;      // + slot*16 + {0..7 V, 8..15 L}
+    float2 *my_partV = reinterpret_cast<float2 *>(ring + (size_t)warp * kRingFloatsPerWarp);  // [NG][BX]
+    float2 *my_partL = my_partV + NG * BX;
+    // lanes 0-3 fetch the Viterbi mailbox row (4 x 16 B), lanes 4-7 the log-sum row
+    const bool qfetch = (lane < 4 && DO_V) || (lane >= 4 && lane < 8 && DO_L);
+    const bool qcheck = (lane < 8 && DO_V) || (lane >= 8 && lane < 16 && DO_L);
     // solver mapping: warp -> (semiring, track), lane -> column
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
     const bool s_nok = (n0 + sn) < N;
+    const long long row_step = (long long)NW * p.sy;
+    const long long q_step = (long long)NW * p.Npad;
 
-    for (int J = nb - 1 - k; J >= 0; J -= p.K) {
+    int owned_idx = 0;
+    for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
         const int x0 = J * BX;
         const int ncols = min(BX, T - x0);
+        TKB_STAMP(0);
 
         // ---- 0. prefetch the diagonal block, transposed to [track][row][col] --------------
         for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
@@ -150,67 +178,74 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int R = T - (x0 + BX);
         const int myrows = R > warp ? (R - warp + NW - 1) / NW : 0;
         if (myrows > 0) {
-            const float *src[2];
-            int nbytes[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = x0 + 2 * cpair + j;  // always < T here: a far field exists only below full blocks
-                nbytes[j] = nvalid * 4;
-                src[j] = nvalid > 0 ? p.Sbase + (long long)col * p.sx + nq : p.Sbase;
+            // running source pointers of the next row to issue (all 32 columns are valid: a far field
+            // exists only below full blocks)
+            const float *sp0 = p.Sbase, *sp1 = p.Sbase;
+            if (nvalid > 0) {
+                sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - warp) * p.sy + nq;
+                sp1 = sp0 + p.sx;
             }
-            auto issue = [&](int t) {
-                const long long yoff = nvalid > 0 ? (long long)(T - 1 - (warp + t * NW)) * p.sy : 0;
-                float *dst = my_ring + (size_t)(t % SLOTS) * 2 * 128;
+            const long long sstep = nvalid > 0 ? row_step : 0;
+            const unsigned long long *qp =
+                (lane < 4 ? mboxV : mboxL) + (size_t)(T - 1 - warp) * p.Npad + n0 + 2 * (lane & 3);
+            const int nbytes = nvalid * 4;
+            int ti = 0;  // next row to issue
+            auto issue = [&]() {
+                float *dst = my_ring + (ti & (SLOTS - 1)) * 256;
+                if (A16) {
+                    cp_async16(dst, sp0, nbytes);
+                    cp_async16(dst + 128, sp1, nbytes);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (A16) {
-                        cp_async16(dst + j * 128, src[j] + yoff, nbytes[j]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            cp_async4(dst + j * 128 + c, src[j] + yoff + (c < nvalid ? c : 0), c < nvalid ? 4 : 0);
+                    for (int c = 0; c < 4; ++c) {
+                        cp_async4(dst + c, sp0 + (c < nvalid ? c : 0), c < nvalid ? 4 : 0);
+                        cp_async4(dst + 128 + c, sp1 + (c < nvalid ? c : 0), c < nvalid ? 4 : 0);
                     }
                 }
+                if (qfetch) cp_async16(my_q + (ti & (SLOTS - 1)) * 16 + 2 * lane, qp, 16);
+                sp0 -= sstep;
+                sp1 -= sstep;
+                qp -= q_step;
+                ++ti;
             };
-            constexpr int D = SLOTS - 1;
 #pragma unroll
             for (int t = 0; t < D; ++t) {
-                if (t < myrows) issue(t);
+                if (t < myrows) issue();
                 cp_async_commit();
             }
-            // mailbox: lanes 0-7 fetch the Viterbi row, lanes 8-15 the log-sum row
-            const bool poller = (lane < 8 && DO_V) || (lane >= 8 && lane < 16 && DO_L);
-            const unsigned long long *wbase = (lane < 8 ? mboxV : mboxL) + n0 + (lane & 7);
-            unsigned long long word = 0;
-            if (poller) word = ld_relaxed_u64(wbase + (size_t)(T - 1 - warp) * p.Npad);
+            int y = T - 1 - warp;
             for (int tb = 0; tb < myrows; tb += CH) {
                 float xl[CH][2][4];
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
                     const int t = tb + i;
                     if (t < myrows) {  // warp-uniform
-                        const int y = T - 1 - (warp + t * NW);
-                        if (t + D < myrows) issue(t + D);
+                        if (ti < myrows) issue();
                         cp_async_commit();
-                        // -- q[y] of my tracks
-                        bool ok = !poller || (unsigned)(word >> 32) == epoch;
-                        if (!__all_sync(kFull, ok)) {
-                            if (!ok) word = poll_slow(wbase + (size_t)y * p.Npad, epoch, p.status);
+                        cp_async_wait<D>();
+                        __syncwarp();
+                        const int slot = t & (SLOTS - 1);
+                        // -- q[y] of my tracks: lanes 0-7 hold the Viterbi words, 8-15 the log-sum words
+                        unsigned long long word = 0;
+                        if (lane < 16) word = my_q[slot * 16 + lane];
+                        const bool ok = !qcheck || (unsigned)(word >> 32) == epoch;
+                        if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
+                            if (!ok)
+                                word = poll_slow((lane < 8 ? mboxV : mboxL) + (size_t)y * p.Npad + n0 + (lane & 7),
+                                                 epoch, p.status);
                         }
                         const float qval = __uint_as_float((unsigned)word);
-                        if (poller && t + 1 < myrows) word = ld_relaxed_u64(wbase + (size_t)(y - NW) * p.Npad);
                         float qv[4], ql[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (DO_V) qv[c] = __shfl_sync(kFull, qval, quad * 4 + c);
                             if (DO_L) ql[c] = __shfl_sync(kFull, qval, 8 + quad * 4 + c);
                         }
-                        // -- S(y, my columns, my tracks)
-                        cp_async_wait<D>();
-                        const float *slot = my_ring + (size_t)(t % SLOTS) * 2 * 128;
+                        // -- S(y, my two columns, my four tracks)
+                        const float *slotp = my_ring + slot * 256;
                         float4 a[2];
-                        a[0] = *reinterpret_cast<const float4 *>(slot);
-                        a[1] = *reinterpret_cast<const float4 *>(slot + 128);
+                        a[0] = *reinterpret_cast<const float4 *>(slotp);
+                        a[1] = *reinterpret_cast<const float4 *>(slotp + 128);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
@@ -226,6 +261,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                                 if (DO_L) xl[i][j][c] = fmaf(av[c], kLog2e, ql[c]);
                             }
                         }
+                        y -= NW;
                     } else if (DO_L) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
@@ -251,17 +287,20 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 }
             }
         }
-        // ---- 2. hand the 16 partials to the solver mapping ---------------------------------
+        // ---- 2. hand the 16 partials to the solver mapping (into this warp's drained FIFO) ----
+        cp_async_wait_all();
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const size_t o = ((size_t)warp * NG + quad * 4 + c) * BX + 2 * cpair + j;
-                if (DO_V) mergeV[o] = make_float2(vmax[j][c], __int_as_float(vsel[j][c]));
-                if (DO_L) mergeL[o] = make_float2(lM[j][c], lS[j][c]);
+                const int o = (quad * 4 + c) * BX + 2 * cpair + j;
+                if (DO_V) my_partV[o] = make_float2(vmax[j][c], __int_as_float(vsel[j][c]));
+                if (DO_L) my_partL[o] = make_float2(lM[j][c], lS[j][c]);
             }
-        cp_async_wait_all();
+        TKB_STAMP(1);
         __syncthreads();
+        TKB_STAMP(2);
 
         // ---- 3. diagonal solve: warp = (semiring, track), lane = column --------------------
         const int c = lane;
@@ -273,7 +312,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             int bsel = -1;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const float2 e = mergeV[((size_t)w * NG + sn) * BX + c];
+                const float2 e = reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[sn * BX + c];
                 const int sl = __float_as_int(e.y);
                 const bool better = e.x > best ||
                                     (e.x == best && sl >= 0 &&
@@ -323,7 +362,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             float M = -FLT_MAX;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const float2 e = mergeL[((size_t)w * NG + sn) * BX + c];
+                const float2 e =
+                    reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
                 m[w] = e.x;
                 s[w] = e.y;
                 M = fmaxf(M, e.x);
@@ -368,7 +408,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             }
             if (x < T && s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = vmine * kLn2;
         }
-        __syncthreads();  // merge buffers and diagS are reused by the next owned block
+        TKB_STAMP(3);
+        __syncthreads();  // partials (in the FIFOs) and diagS are reused by the next owned block
     }
 }
 
@@ -398,6 +439,7 @@ static int launch_mode(int mode, const SweepParams &p, int grid, cudaStream_t st
     }
 }
 
+static unsigned long long *g_timeline = nullptr;  // diagnostics build only
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -447,6 +489,7 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
     p.code = out_code;
     p.outv = out_vit;
     p.outl = out_lse;
+    p.timeline = g_timeline;
     if (direction == TKB_BACKWARD) {
         p.Sbase = score;
         p.sx = N;
@@ -493,3 +536,6 @@ extern "C" int tkb_sweep_status(const void *workspace, int *status_host, void *s
     TKB_CUDA(cudaStreamSynchronize(stream));
     return 0;
 }
+
+// diagnostics build only (compile with -DTKB_TIMELINE): device buffer of [grid][64][4] globaltimer stamps
+extern "C" void tkb_debug_set_timeline(unsigned long long *buf) { g_timeline = buf; }
