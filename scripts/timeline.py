@@ -21,7 +21,7 @@ L = _lib.load()
 score, noise = make_inputs("randn", T, N, 1234)
 s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
 grid_max = 148
-tl = torch.zeros((grid_max, 64, 4), dtype=torch.int64, device="cuda")
+tl = torch.zeros((grid_max, 64, 8), dtype=torch.int64, device="cuda")
 L.tkb_debug_set_timeline.argtypes = [ctypes.c_void_p]
 L.tkb_debug_set_timeline(tl.data_ptr())
 for _ in range(3):
@@ -34,20 +34,23 @@ nb = (T + 31) // 32
 K = min(148 // G, nb)
 t0 = t[t > 0].min()
 print(f"T={T} N={N} G={G} K={K} nb={nb}; kernel span {(t.max() - t0) / 1e3:.1f} us")
-# group 0: blocks in chain order
+# stamps (thread 0 = Viterbi warp of track 0): 0 block start | 1 far field done | 2 partials merged (near tile
+# starts) | 3 near tile done (diagonal solve starts) | 4 solve done
 rows = []
 for J in range(nb - 1, -1, -1):
     k = (nb - 1 - J) % K
     idx = (nb - 1 - J) // K
-    st = (t[k, idx] - t0) / 1e3
-    rows.append((J, k, *st))
+    rows.append((J, k, *((t[k, idx, :5] - t0) / 1e3)))
 rows = np.array(rows)
-print("  J  cta  far_start  far_end   solve_start solve_end | far_us wait_sync_us solve_us | chain_gap_us")
-prev_end = None
-for J, k, a, b, c, d in rows[:: max(1, nb // 32)]:
-    print(f"{int(J):4d} {int(k):3d} {a:10.1f} {b:9.1f} {c:11.1f} {d:9.1f} | {b - a:6.1f} {c - b:8.1f} {d - c:8.1f}")
-solve = rows[:, 5] - rows[:, 4]
-gap = rows[1:, 4] - rows[:-1, 5]   # solve start of next block minus solve end of previous block
-print(f"solve_us mean {solve.mean():.2f} min {solve.min():.2f} max {solve.max():.2f}")
-print(f"handoff gap (next solve start - prev solve end) mean {gap.mean():.2f} median {np.median(gap):.2f} max {gap.max():.2f}")
-print(f"far_us mean {np.mean(rows[:, 3] - rows[:, 2]):.2f}; chain per block {(rows[-1, 5] - rows[0, 4]) / (nb - 1):.2f} us")
+print("   J cta    start  far_done   merged near_done solve_done |  far  sync+merge  near  solve | chain step")
+prev = None
+for i, (J, k, a, b, c, d, e) in enumerate(rows):
+    if i % max(1, nb // 32) == 0:
+        step = e - prev if prev is not None else 0.0
+        print(f"{int(J):4d} {int(k):3d} {a:8.1f} {b:9.1f} {c:8.1f} {d:9.1f} {e:10.1f} | {b-a:5.1f} {c-b:8.2f} {d-c:7.2f} {e-d:6.2f} | {step:6.2f}")
+    prev = e
+ends = rows[:, 6]
+print(f"solve_us mean {np.mean(rows[:,6]-rows[:,5]):.2f}  near_us mean {np.mean(rows[:,5]-rows[:,4]):.2f}  "
+      f"sync+merge mean {np.mean(rows[:,4]-rows[:,3]):.2f}")
+print(f"chain per block (solve_done to solve_done): mean {np.mean(np.diff(ends)):.2f} median {np.median(np.diff(ends)):.2f} us;"
+      f" handoff (prev solve_done -> my solve start) mean {np.mean(rows[1:,5]-rows[:-1,6]):.2f} us")

@@ -18,12 +18,19 @@
 //   * tracks are independent -> groups of NG=8 tracks (one 32-byte sector of the
 //     track-innermost layout) form independent pipelines;
 //   * per group, K CTAs own the 32-column blocks round-robin (block J -> CTA
-//     (nb-1-J) mod K).  For its block a CTA first streams the FAR FIELD (all rows
-//     y in later blocks; order-free semiring mat-vec; 16 warps each own every
-//     16th row, cp.async-staged into per-lane shared-memory FIFOs, accumulators
-//     in registers), then merges the 16 partials and runs the sequential
-//     32-step DIAGONAL SOLVE with one warp per (track, semiring), lane = column,
-//     one shuffle per step;
+//     (nb-1-J) mod K).  For its block J a CTA runs four phases:
+//       A  FAR FIELD: all rows y in blocks >= J+2 (order-free semiring mat-vec, the
+//          bulk of the bytes): 16 warps each own every 16th row, cp.async-staged into
+//          per-lane shared-memory FIFOs together with the mailbox row, accumulators
+//          in registers;
+//       B  the 16 partials are merged into the solver mapping: one warp per
+//          (track, semiring), lane = column;
+//       C  NEAR TILE: the 32 rows of block J+1 are consumed by the solver warps
+//          directly, in batches of 8 as the previous owner publishes them;
+//       D  DIAGONAL SOLVE: 31 dependent steps, one shuffle each.  The log-sum chain
+//          carries (M, S) pairs (value = M + log2 S) so no log sits on the chain, the
+//          skip weight is folded into the coefficient of the row right above a
+//          column, and rows are published in batches of 8 (one lg2 per batch);
 //   * solved rows are broadcast to the other CTAs of the group through a
 //     global-memory mailbox of 64-bit words {fp32 value, epoch tag}: one relaxed
 //     store publishes, one relaxed load observes (no fence, no flag, no reset).
@@ -38,18 +45,21 @@ constexpr int NW = 16;     // warps per CTA: far field 16 row-slices; solve 8 tr
 constexpr int NT = NW * 32;
 constexpr int SLOTS = 8;   // per-warp FIFO depth (rows); SLOTS-1 rows in flight
 constexpr int CH = 4;      // rows per log-sum-exp rescale chunk
+constexpr int PB = 8;      // rows per publish batch
 
-// shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) | diagonal block.
+// shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
+// diagonal block | near tile (block J+1 rows x block J columns), both transposed to [track][row][col].
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 32 * 4;
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
 constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 16;
-constexpr size_t kDiagFloats = (size_t)NG * BX * BX;
-constexpr size_t kSweepSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + kDiagFloats * 4;
+constexpr size_t kTileFloats = (size_t)NG * BX * BX;
+constexpr size_t kSweepSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + 2 * kTileFloats * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
+#define TKB_TIMELINE_STAMPS 8
 
 struct SweepParams {
     const float *Sbase;    // &S(0,0) in mirrored coordinates
@@ -62,7 +72,7 @@ struct SweepParams {
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
     float *outl;     // [T][N] or null
-    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][4] globaltimer stamps
+    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][8] globaltimer stamps
 };
 
 // Wait until the mailbox word carries this launch's epoch.  A protocol bug (or a
@@ -82,26 +92,29 @@ __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w
         }
     }
 }
-__device__ __forceinline__ float poll_value(const unsigned long long *w, unsigned epoch, int *status) {
-    unsigned long long v = ld_relaxed_u64(w);
-    if ((unsigned)(v >> 32) != epoch) v = poll_slow(w, epoch, status);
-    return __uint_as_float((unsigned)v);
-}
 __device__ __forceinline__ void publish(unsigned long long *w, float val, unsigned epoch) {
     st_relaxed_u64(w, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val));
 }
 
 #ifdef TKB_TIMELINE
-#define TKB_STAMP(slot)                                                                                   \
-    do {                                                                                                  \
-        if (threadIdx.x == 0 && p.timeline && owned_idx < 64)                                             \
-            p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * 4 + (slot)] = globaltimer_ns();            \
+#define TKB_STAMP(slot)                                                                                     \
+    do {                                                                                                    \
+        if (threadIdx.x == 0 && p.timeline && owned_idx < 64)                                               \
+            p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + (slot)] = globaltimer_ns(); \
     } while (0)
 #else
 #define TKB_STAMP(slot) \
     do {                \
     } while (0)
 #endif
+
+// (M, S) <- (M, S) (+) sb * 2^a        value = M + log2(S); one ex2: one of the two exponents is 0
+__device__ __forceinline__ void lse_push(float &M, float &S, float a, float sb) {
+    const float d = M - a;
+    const float e1 = ex2f(-fabsf(d));
+    S = (d < 0.0f) ? fmaf(S, e1, sb) : fmaf(sb, e1, S);
+    M = fmaxf(M, a);
+}
 
 template <int DIR, bool A16, int MODE>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
@@ -113,6 +126,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     float *ring = reinterpret_cast<float *>(smem_raw);
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *diagS = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);  // [NG][BX rows][BX cols]
+    float *nearS = diagS + kTileFloats;                                             // [NG][BX rows][BX cols]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -138,6 +152,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
     const bool s_nok = (n0 + sn) < N;
+    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + n0 + sn;  // + row * Npad
     const long long row_step = (long long)NW * p.sy;
     const long long q_step = (long long)NW * p.Npad;
 
@@ -145,41 +160,44 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
         const int x0 = J * BX;
         const int ncols = min(BX, T - x0);
+        const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of the near tile (block J+1)
         TKB_STAMP(0);
 
-        // ---- 0. prefetch the diagonal block, transposed to [track][row][col] --------------
+        // ---- 0. prefetch the diagonal block and the near tile, transposed to [track][row][col] ----
         for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
             const int n = i & 7, c = (i >> 3) & 31, r = i >> 8;
-            if (r > c && r < ncols && (n0 + n) < N)
-                cp_async4(&diagS[(n * BX + r) * BX + c],
-                          p.Sbase + (long long)(x0 + c) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
+            if ((n0 + n) < N) {
+                const float *src = p.Sbase + (long long)(x0 + c) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
+                if (r > c && r < ncols) cp_async4(&diagS[(n * BX + r) * BX + c], src, 4);
+                if (r < nr) cp_async4(&nearS[(n * BX + r) * BX + c], src + (long long)BX * p.sy, 4);
+            }
         }
         cp_async_commit();
         // unary + skip weights of my solver column (kept in registers across the far field)
-        const int sx_ = x0 + lane;
+        const int c = lane;
+        const int x = x0 + c;
         float s_d = 0.0f, s_eta = 0.0f;
-        if (sx_ < T && s_nok) {
-            s_d = __ldg(p.Sbase + (long long)sx_ * (p.sx + p.sy) + n0 + sn);
-            if (sx_ < T - 1) s_eta = __ldg(p.etabase + (long long)sx_ * p.se + n0 + sn);
+        if (x < T && s_nok) {
+            s_d = __ldg(p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn);
+            if (x < T - 1) s_eta = __ldg(p.etabase + (long long)x * p.se + n0 + sn);
         }
 
-        // ---- 1. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th --------------
+        // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th --------------
         float vmax[2][4], lM[2][4], lS[2][4];
         int vsel[2][4];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                vmax[j][c] = -INFINITY;
-                vsel[j][c] = -1;
-                lM[j][c] = -FLT_MAX;
-                lS[j][c] = 0.0f;
+            for (int q = 0; q < 4; ++q) {
+                vmax[j][q] = -INFINITY;
+                vsel[j][q] = -1;
+                lM[j][q] = -FLT_MAX;
+                lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + BX);
+        const int R = T - (x0 + 2 * BX);
         const int myrows = R > warp ? (R - warp + NW - 1) / NW : 0;
         if (myrows > 0) {
-            // running source pointers of the next row to issue (all 32 columns are valid: a far field
-            // exists only below full blocks)
+            // running source pointers of the next row to issue (all 32 columns are valid here)
             const float *sp0 = p.Sbase, *sp1 = p.Sbase;
             if (nvalid > 0) {
                 sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - warp) * p.sy + nq;
@@ -197,9 +215,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                     cp_async16(dst + 128, sp1, nbytes);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        cp_async4(dst + c, sp0 + (c < nvalid ? c : 0), c < nvalid ? 4 : 0);
-                        cp_async4(dst + 128 + c, sp1 + (c < nvalid ? c : 0), c < nvalid ? 4 : 0);
+                    for (int q = 0; q < 4; ++q) {
+                        cp_async4(dst + q, sp0 + (q < nvalid ? q : 0), q < nvalid ? 4 : 0);
+                        cp_async4(dst + 128 + q, sp1 + (q < nvalid ? q : 0), q < nvalid ? 4 : 0);
                     }
                 }
                 if (qfetch) cp_async16(my_q + (ti & (SLOTS - 1)) * 16 + 2 * lane, qp, 16);
@@ -237,9 +255,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         const float qval = __uint_as_float((unsigned)word);
                         float qv[4], ql[4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (DO_V) qv[c] = __shfl_sync(kFull, qval, quad * 4 + c);
-                            if (DO_L) ql[c] = __shfl_sync(kFull, qval, 8 + quad * 4 + c);
+                        for (int q = 0; q < 4; ++q) {
+                            if (DO_V) qv[q] = __shfl_sync(kFull, qval, quad * 4 + q);
+                            if (DO_L) ql[q] = __shfl_sync(kFull, qval, 8 + quad * 4 + q);
                         }
                         // -- S(y, my two columns, my four tracks)
                         const float *slotp = my_ring + slot * 256;
@@ -250,15 +268,15 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         for (int j = 0; j < 2; ++j) {
                             const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
+                            for (int q = 0; q < 4; ++q) {
                                 if (DO_V) {
-                                    const float xv = qv[c] + av[c];
+                                    const float xv = qv[q] + av[q];
                                     const bool tk =
-                                        (DIR == TKB_BACKWARD) ? (xv >= vmax[j][c]) : (xv > vmax[j][c]);
-                                    vmax[j][c] = tk ? xv : vmax[j][c];
-                                    vsel[j][c] = tk ? y : vsel[j][c];
+                                        (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
+                                    vmax[j][q] = tk ? xv : vmax[j][q];
+                                    vsel[j][q] = tk ? y : vsel[j][q];
                                 }
-                                if (DO_L) xl[i][j][c] = fmaf(av[c], kLog2e, ql[c]);
+                                if (DO_L) xl[i][j][q] = fmaf(av[q], kLog2e, ql[q]);
                             }
                         }
                         y -= NW;
@@ -266,50 +284,48 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) xl[i][j][c] = -FLT_MAX;
+                            for (int q = 0; q < 4; ++q) xl[i][j][q] = -FLT_MAX;
                     }
                 }
                 if (DO_L) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float m = xl[0][j][c];
+                        for (int q = 0; q < 4; ++q) {
+                            float m = xl[0][j][q];
 #pragma unroll
-                            for (int i = 1; i < CH; ++i) m = fmaxf(m, xl[i][j][c]);
-                            const float Mn = fmaxf(lM[j][c], m);
-                            float acc = lS[j][c] * ex2f(lM[j][c] - Mn);
+                            for (int i = 1; i < CH; ++i) m = fmaxf(m, xl[i][j][q]);
+                            const float Mn = fmaxf(lM[j][q], m);
+                            float acc = lS[j][q] * ex2f(lM[j][q] - Mn);
 #pragma unroll
-                            for (int i = 0; i < CH; ++i) acc += ex2f(xl[i][j][c] - Mn);
-                            lS[j][c] = acc;
-                            lM[j][c] = Mn;
+                            for (int i = 0; i < CH; ++i) acc += ex2f(xl[i][j][q] - Mn);
+                            lS[j][q] = acc;
+                            lM[j][q] = Mn;
                         }
                 }
             }
         }
-        // ---- 2. hand the 16 partials to the solver mapping (into this warp's drained FIFO) ----
+        // ---- B. hand the 16 partials to the solver mapping (via this warp's drained FIFO) --------
         cp_async_wait_all();
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int o = (quad * 4 + c) * BX + 2 * cpair + j;
-                if (DO_V) my_partV[o] = make_float2(vmax[j][c], __int_as_float(vsel[j][c]));
-                if (DO_L) my_partL[o] = make_float2(lM[j][c], lS[j][c]);
+            for (int q = 0; q < 4; ++q) {
+                const int o = (quad * 4 + q) * BX + 2 * cpair + j;
+                if (DO_V) my_partV[o] = make_float2(vmax[j][q], __int_as_float(vsel[j][q]));
+                if (DO_L) my_partL[o] = make_float2(lM[j][q], lS[j][q]);
             }
         TKB_STAMP(1);
         __syncthreads();
-        TKB_STAMP(2);
 
-        // ---- 3. diagonal solve: warp = (semiring, track), lane = column --------------------
-        const int c = lane;
-        const int x = x0 + c;
         const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
-        const bool has_next = (x0 + BX) <= T - 1;  // a later block exists -> skip candidate of the top column
+        const bool active = x < T;
+        // near-tile mailbox polling: lane i < PB fetches row i of the current batch
         if (!s_is_lse && DO_V) {
+            // ================= Viterbi: (max,+), bit-exact fp32 =================================
             float best = -INFINITY;
-            int bsel = -1;
+            int bsel = -1;  // mirrored y of the best interval so far, -1 = none / skip
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const float2 e = reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[sn * BX + c];
@@ -326,90 +342,162 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = diagS[(sn * BX + r) * BX + c];
             const float dr = relu_mask(s_d);
-            float qprev = 0.0f, qmine = 0.0f;
-            if (has_next) qprev = poll_value(mboxV + (size_t)(x0 + BX) * p.Npad + n0 + sn, epoch, p.status);
+            if (x == T - 1) best = 0.0f;  // terminal column: no candidates, q = relu(S[T-1,T-1])  (0 + dr == dr)
+            TKB_STAMP(2);
+            // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX (lane i fetches the mailbox word of row i) ----
+            unsigned long long word = 0;
+            const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
+            if (lane < nr) word = ld_relaxed_u64(wrow);
+            for (int b = (nr - 1) / PB; b >= 0 && nr > 0; --b) {
+                if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                    word = poll_slow(wrow, epoch, p.status);
+                const float val = __uint_as_float((unsigned)word);
 #pragma unroll
-            for (int r = BX - 1; r >= 0; --r) {
-                if (r < ncols) {
-                    const float skipc = qprev + s_eta;
-                    const bool tk = best > skipc;  // skip is candidate 0: it wins every tie
-                    const float m = tk ? best : skipc;
-                    const float qfin = (x == T - 1) ? dr : (m + dr);
-                    const float qb = __shfl_sync(kFull, qfin, r);
-                    if (c == r) {
-                        qmine = qfin;
-                        if (!tk) bsel = -1;
-                        publish(mboxV + (size_t)x * p.Npad + n0 + sn, qb, epoch);
-                    }
-                    if (c < r) {
-                        const float xx = qb + sreg[r];
-                        const bool t2 = (DIR == TKB_BACKWARD) ? (xx >= best) : (xx > best);
-                        if (t2) {
-                            best = xx;
-                            bsel = x0 + r;
+                for (int i = PB - 1; i >= 0; --i) {
+                    const int r = b * PB + i;
+                    if (r < nr) {
+                        const float qb = __shfl_sync(kFull, val, r);
+                        const float s = nearS[(sn * BX + r) * BX + c];
+                        const int y = x0 + BX + r;
+                        const float xi = qb + s;
+                        if (r == 0 && c == BX - 1) {
+                            // the row right above this column also offers the skip; reference candidate order:
+                            // skip first, then intervals by increasing end (BACKWARD) / increasing begin (FORWARD)
+                            const float xk = qb + s_eta;
+                            if (DIR == TKB_BACKWARD) {
+                                if (fmaxf(xk, xi) >= best) bsel = (xk >= xi) ? -1 : y;
+                            } else {
+                                if (xi > best) bsel = y;
+                                if (xk >= fmaxf(best, xi)) bsel = -1;
+                            }
+                            best = fmaxf(best, fmaxf(xi, xk));
+                        } else {
+                            const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
+                            bsel = tk ? y : bsel;
+                            best = fmaxf(best, xi);
                         }
                     }
-                    if (c == r - 1) qprev = qb;
                 }
             }
-            if (x < T && s_nok) {
+            TKB_STAMP(3);
+            // ---- D. diagonal solve ------------------------------------------------------------------
+            float qmine = best + dr;  // final for lane ncols-1 already; other lanes overwrite below
+#pragma unroll
+            for (int e = BX - 1; e >= 1; --e) {
+                if (e < ncols) {
+                    const float qfin = best + dr;
+                    const float qb = __shfl_sync(kFull, qfin, e);
+                    if (c == e) qmine = qfin;
+                    const float xi = qb + sreg[e];
+                    if (c == e - 1) {
+                        const float xk = qb + s_eta;
+                        if (DIR == TKB_BACKWARD) {
+                            if (fmaxf(xk, xi) >= best) bsel = (xk >= xi) ? -1 : x0 + e;
+                        } else {
+                            if (xi > best) bsel = x0 + e;
+                            if (xk >= fmaxf(best, xi)) bsel = -1;
+                        }
+                        best = fmaxf(best, fmaxf(xi, xk));
+                    } else if (c < e - 1) {
+                        const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
+                        bsel = tk ? x0 + e : bsel;
+                        best = fmaxf(best, xi);
+                    }
+                }
+                if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active)
+                    publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
+            }
+            if (c == 0) qmine = best + dr;
+            if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
+            if (active && s_nok) {
                 const int osel = bsel < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel : T - 1 - bsel);
                 p.code[(size_t)(n0 + sn) * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
                 if (p.outv) p.outv[(size_t)pos * N + n0 + sn] = qmine;
             }
         } else if (s_is_lse && DO_L) {
-            float m[NW], s[NW];
-            float M = -FLT_MAX;
+            // ================= log-sum: (logsumexp,+) in the log2 domain, (M, S) pairs ===============
+            float M = -FLT_MAX, S = 0.0f;
+            {
+                float m[NW], s[NW];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const float2 e =
-                    reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
-                m[w] = e.x;
-                s[w] = e.y;
-                M = fmaxf(M, e.x);
+                for (int w = 0; w < NW; ++w) {
+                    const float2 e =
+                        reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
+                    m[w] = e.x;
+                    s[w] = e.y;
+                    M = fmaxf(M, e.x);
+                }
+#pragma unroll
+                for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
             }
-            float S = 0.0f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
+            const float sp2 = softplus_ref(s_d) * kLog2e;
+            const float eta2 = s_eta * kLog2e;
             float sreg[BX];
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = diagS[(sn * BX + r) * BX + c] * kLog2e;
-            const float sp2 = softplus_ref(s_d) * kLog2e;
-            const float eta2 = s_eta * kLog2e;
-            float qprev = 0.0f, vmine = 0.0f;
-            if (has_next) qprev = poll_value(mboxL + (size_t)(x0 + BX) * p.Npad + n0 + sn, epoch, p.status);
+            // fold the skip into the coefficient of the row right above my column:
+            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
+            {
+                float sp = 0.0f;
 #pragma unroll
-            for (int r = BX - 1; r >= 0; --r) {
-                if (r < ncols) {
-                    float v2 = 0.0f;
-                    if (c == r) {
-                        if (x == T - 1) {
-                            v2 = sp2;
-                        } else {
-                            const float xs = qprev + eta2;
-                            const float e = ex2f(-fabsf(M - xs));
-                            const float tot = (xs > M) ? fmaf(S, e, 1.0f) : (S + e);
-                            v2 = (fmaxf(M, xs) + lg2f(tot)) + sp2;
+                for (int r = 1; r < BX; ++r)
+                    if (c == r - 1) sp = sreg[r];
+                const float mx = fmaxf(sp, eta2);
+                const float comb = mx + lg2f(1.0f + ex2f(-fabsf(sp - eta2)));
+#pragma unroll
+                for (int r = 1; r < BX; ++r)
+                    if (c == r - 1) sreg[r] = comb;
+            }
+            if (x == T - 1) {  // terminal column: value = softplus(S[T-1,T-1])
+                M = 0.0f;
+                S = 1.0f;
+            }
+            TKB_STAMP(2);
+            // ---- C. near tile (lane i fetches the mailbox word of row i) ---------------------------------
+            unsigned long long word = 0;
+            const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
+            if (lane < nr) word = ld_relaxed_u64(wrow);
+            for (int b = (nr - 1) / PB; b >= 0 && nr > 0; --b) {
+                if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                    word = poll_slow(wrow, epoch, p.status);
+                const float val = __uint_as_float((unsigned)word);
+#pragma unroll
+                for (int i = PB - 1; i >= 0; --i) {
+                    const int r = b * PB + i;
+                    if (r < nr) {
+                        const float vb = __shfl_sync(kFull, val, r);
+                        float s2 = nearS[(sn * BX + r) * BX + c] * kLog2e;
+                        if (r == 0 && c == BX - 1) {
+                            const float mx = fmaxf(s2, eta2);
+                            s2 = mx + lg2f(1.0f + ex2f(-fabsf(s2 - eta2)));
                         }
+                        lse_push(M, S, vb + s2, 1.0f);
                     }
-                    const float vb = __shfl_sync(kFull, v2, r);
-                    if (c == r) {
-                        vmine = v2;
-                        publish(mboxL + (size_t)x * p.Npad + n0 + sn, vb, epoch);
-                    }
-                    if (c < r) {
-                        const float xlv = vb + sreg[r];
-                        const float e = ex2f(-fabsf(M - xlv));
-                        S = (xlv > M) ? fmaf(S, e, 1.0f) : (S + e);
-                        M = fmaxf(M, xlv);
-                    }
-                    if (c == r - 1) qprev = vb;
                 }
             }
-            if (x < T && s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = vmine * kLn2;
+            TKB_STAMP(3);
+            // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to lanes c < e ----------
+#pragma unroll
+            for (int e = BX - 1; e >= 1; --e) {
+                if (e < ncols) {
+                    const float Mb = __shfl_sync(kFull, M + sp2, e);
+                    const float sb = __shfl_sync(kFull, S, e);
+                    if (c < e) lse_push(M, S, Mb + sreg[e], sb);
+                }
+                if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active) {
+                    const float v2 = (M + sp2) + lg2f(S);
+                    publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
+                    if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
+                }
+            }
+            if (c < PB && active) {
+                const float v2 = (M + sp2) + lg2f(S);
+                publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
+                if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
+            }
         }
-        TKB_STAMP(3);
-        __syncthreads();  // partials (in the FIFOs) and diagS are reused by the next owned block
+        TKB_STAMP(4);
+        __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
     }
 }
 
