@@ -163,14 +163,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of the near tile (block J+1)
         TKB_STAMP(0);
 
-        // ---- 0. prefetch the diagonal block and the near tile, transposed to [track][row][col] ----
+        // ---- 0. prefetch the diagonal block and the near tile, transposed to [track][row][col];
+        //         rows beyond T (only in the last one or two blocks) are filled with -inf = "no candidate"
         for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
-            const int n = i & 7, c = (i >> 3) & 31, r = i >> 8;
-            if ((n0 + n) < N) {
-                const float *src = p.Sbase + (long long)(x0 + c) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
-                if (r > c && r < ncols) cp_async4(&diagS[(n * BX + r) * BX + c], src, 4);
-                if (r < nr) cp_async4(&nearS[(n * BX + r) * BX + c], src + (long long)BX * p.sy, 4);
+            const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
+            const bool nok = (n0 + n) < N;
+            const float *src = p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
+            if (r > cc) {
+                if (r < ncols && nok) cp_async4(&diagS[(n * BX + r) * BX + cc], src, 4);
+                else diagS[(n * BX + r) * BX + cc] = -INFINITY;
             }
+            if (r < nr && nok) cp_async4(&nearS[(n * BX + r) * BX + cc], src + (long long)BX * p.sy, 4);
+            else if (nr > 0) nearS[(n * BX + r) * BX + cc] = -INFINITY;
         }
         cp_async_commit();
         // unary + skip weights of my solver column (kept in registers across the far field)
@@ -321,7 +325,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 
         const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
         const bool active = x < T;
-        // near-tile mailbox polling: lane i < PB fetches row i of the current batch
+        // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows
+        // or columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
+        // near-tile mailbox words: lane i fetches row i (one round trip for everything already published)
+        unsigned long long word = 0;
+        const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
+        const bool solver_on = s_is_lse ? DO_L : DO_V;
+        if (solver_on && lane < nr) word = ld_relaxed_u64(wrow);
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
             float best = -INFINITY;
@@ -340,75 +350,54 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             }
             float sreg[BX];
 #pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = diagS[(sn * BX + r) * BX + c];
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
             const float dr = relu_mask(s_d);
-            if (x == T - 1) best = 0.0f;  // terminal column: no candidates, q = relu(S[T-1,T-1])  (0 + dr == dr)
+            // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
+            if (x == T - 1) best = -0.0f;
+            const float eta_top = (c == BX - 1 && nr > 0) ? s_eta : -INFINITY;  // skip from row x0+BX
             TKB_STAMP(2);
-            // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX (lane i fetches the mailbox word of row i) ----
-            unsigned long long word = 0;
-            const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
-            if (lane < nr) word = ld_relaxed_u64(wrow);
-            for (int b = (nr - 1) / PB; b >= 0 && nr > 0; --b) {
-                if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
-                    word = poll_slow(wrow, epoch, p.status);
-                const float val = __uint_as_float((unsigned)word);
+            // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX ------------------------------------------
+            if (nr > 0) {
+                for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                        word = poll_slow(wrow, epoch, p.status);
+                    const float val = __uint_as_float((unsigned)word);
 #pragma unroll
-                for (int i = PB - 1; i >= 0; --i) {
-                    const int r = b * PB + i;
-                    if (r < nr) {
+                    for (int i = PB - 1; i >= 0; --i) {
+                        const int r = b * PB + i;
                         const float qb = __shfl_sync(kFull, val, r);
-                        const float s = nearS[(sn * BX + r) * BX + c];
-                        const int y = x0 + BX + r;
-                        const float xi = qb + s;
-                        if (r == 0 && c == BX - 1) {
-                            // the row right above this column also offers the skip; reference candidate order:
-                            // skip first, then intervals by increasing end (BACKWARD) / increasing begin (FORWARD)
-                            const float xk = qb + s_eta;
-                            if (DIR == TKB_BACKWARD) {
-                                if (fmaxf(xk, xi) >= best) bsel = (xk >= xi) ? -1 : y;
-                            } else {
-                                if (xi > best) bsel = y;
-                                if (xk >= fmaxf(best, xi)) bsel = -1;
-                            }
-                            best = fmaxf(best, fmaxf(xi, xk));
-                        } else {
-                            const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
-                            bsel = tk ? y : bsel;
-                            best = fmaxf(best, xi);
-                        }
-                    }
-                }
-            }
-            TKB_STAMP(3);
-            // ---- D. diagonal solve ------------------------------------------------------------------
-            float qmine = best + dr;  // final for lane ncols-1 already; other lanes overwrite below
-#pragma unroll
-            for (int e = BX - 1; e >= 1; --e) {
-                if (e < ncols) {
-                    const float qfin = best + dr;
-                    const float qb = __shfl_sync(kFull, qfin, e);
-                    if (c == e) qmine = qfin;
-                    const float xi = qb + sreg[e];
-                    if (c == e - 1) {
-                        const float xk = qb + s_eta;
-                        if (DIR == TKB_BACKWARD) {
-                            if (fmaxf(xk, xi) >= best) bsel = (xk >= xi) ? -1 : x0 + e;
-                        } else {
-                            if (xi > best) bsel = x0 + e;
-                            if (xk >= fmaxf(best, xi)) bsel = -1;
-                        }
-                        best = fmaxf(best, fmaxf(xi, xk));
-                    } else if (c < e - 1) {
+                        const float xi = qb + nearS[(sn * BX + r) * BX + c];
                         const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
-                        bsel = tk ? x0 + e : bsel;
+                        bsel = tk ? x0 + BX + r : bsel;
                         best = fmaxf(best, xi);
                     }
                 }
+                // the skip out of the top column: candidate 0 of the reference, so it wins every tie
+                const float xk = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top;
+                bsel = (xk >= best) ? -1 : bsel;
+                best = fmaxf(best, xk);
+            }
+            TKB_STAMP(3);
+            // ---- D. diagonal solve: value chain = FADD -> SHFL -> FADD -> FMNMX ------------------
+            float qmine = 0.0f;
+#pragma unroll
+            for (int e = BX - 1; e >= 1; --e) {
+                const float qfin = best + dr;
+                const float qb = __shfl_sync(kFull, qfin, e);
+                qmine = (c == e) ? qfin : qmine;
+                const float xi = qb + sreg[e];                              // -inf for lanes c >= e
+                const float xk = (c == e - 1) ? qb + s_eta : -INFINITY;    // skip x -> x+1
+                const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
+                const float b1 = fmaxf(best, xi);
+                bsel = tk ? x0 + e : bsel;
+                bsel = (xk >= b1) ? -1 : bsel;
+                best = fmaxf(b1, xk);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active)
                     publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
             }
-            if (c == 0) qmine = best + dr;
+            qmine = (c == 0) ? best + dr : qmine;
             if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
+            TKB_STAMP(4);
             if (active && s_nok) {
                 const int osel = bsel < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel : T - 1 - bsel);
                 p.code[(size_t)(n0 + sn) * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
@@ -434,56 +423,52 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const float eta2 = s_eta * kLog2e;
             float sreg[BX];
 #pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = diagS[(sn * BX + r) * BX + c] * kLog2e;
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
             // fold the skip into the coefficient of the row right above my column:
             // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
             {
-                float sp = 0.0f;
+                float sp = -INFINITY;
 #pragma unroll
-                for (int r = 1; r < BX; ++r)
-                    if (c == r - 1) sp = sreg[r];
+                for (int r = 1; r < BX; ++r) sp = (c == r - 1) ? sreg[r] : sp;
                 const float mx = fmaxf(sp, eta2);
-                const float comb = mx + lg2f(1.0f + ex2f(-fabsf(sp - eta2)));
+                const float comb = (sp == -INFINITY) ? sp : mx + lg2f(1.0f + ex2f(-fabsf(sp - eta2)));
 #pragma unroll
-                for (int r = 1; r < BX; ++r)
-                    if (c == r - 1) sreg[r] = comb;
+                for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
             }
             if (x == T - 1) {  // terminal column: value = softplus(S[T-1,T-1])
                 M = 0.0f;
                 S = 1.0f;
             }
-            TKB_STAMP(2);
-            // ---- C. near tile (lane i fetches the mailbox word of row i) ---------------------------------
-            unsigned long long word = 0;
-            const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
-            if (lane < nr) word = ld_relaxed_u64(wrow);
-            for (int b = (nr - 1) / PB; b >= 0 && nr > 0; --b) {
-                if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
-                    word = poll_slow(wrow, epoch, p.status);
-                const float val = __uint_as_float((unsigned)word);
+            const float eta_top = (c == BX - 1 && nr > 0) ? eta2 : -INFINITY;
+#ifdef TKB_TIMELINE
+            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
+                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 5] = globaltimer_ns();
+#endif
+            // ---- C. near tile -----------------------------------------------------------------------
+            if (nr > 0) {
+                for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                        word = poll_slow(wrow, epoch, p.status);
+                    const float val = __uint_as_float((unsigned)word);
 #pragma unroll
-                for (int i = PB - 1; i >= 0; --i) {
-                    const int r = b * PB + i;
-                    if (r < nr) {
+                    for (int i = PB - 1; i >= 0; --i) {
+                        const int r = b * PB + i;
                         const float vb = __shfl_sync(kFull, val, r);
-                        float s2 = nearS[(sn * BX + r) * BX + c] * kLog2e;
-                        if (r == 0 && c == BX - 1) {
-                            const float mx = fmaxf(s2, eta2);
-                            s2 = mx + lg2f(1.0f + ex2f(-fabsf(s2 - eta2)));
-                        }
-                        lse_push(M, S, vb + s2, 1.0f);
+                        lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);
                     }
                 }
+                lse_push(M, S, __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top, 1.0f);
             }
-            TKB_STAMP(3);
-            // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to lanes c < e ----------
+#ifdef TKB_TIMELINE
+            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
+                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 6] = globaltimer_ns();
+#endif
+            // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
 #pragma unroll
             for (int e = BX - 1; e >= 1; --e) {
-                if (e < ncols) {
-                    const float Mb = __shfl_sync(kFull, M + sp2, e);
-                    const float sb = __shfl_sync(kFull, S, e);
-                    if (c < e) lse_push(M, S, Mb + sreg[e], sb);
-                }
+                const float Mb = __shfl_sync(kFull, M + sp2, e);
+                const float sb = __shfl_sync(kFull, S, e);
+                lse_push(M, S, Mb + sreg[e], sb);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active) {
                     const float v2 = (M + sp2) + lg2f(S);
                     publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
@@ -495,8 +480,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
                 if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
             }
+#ifdef TKB_TIMELINE
+            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
+                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 7] = globaltimer_ns();
+#endif
         }
-        TKB_STAMP(4);
         __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
     }
 }
