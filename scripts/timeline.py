@@ -40,17 +40,19 @@ rows = []
 for J in range(nb - 1, -1, -1):
     k = (nb - 1 - J) % K
     idx = (nb - 1 - J) // K
-    rows.append((J, k, *((t[k, idx, :5] - t0) / 1e3)))
+    rows.append((J, k, *((t[k, idx, :8] - t0) / 1e3)))
 rows = np.array(rows)
-print("   J cta    start  far_done   merged near_done solve_done |  far  sync+merge  near  solve | chain step")
-prev = None
-for i, (J, k, a, b, c, d, e) in enumerate(rows):
+print("   J cta    start  far_done | V:merged near_done solve_done | L:setup  near_done solve_done | V solve  L solve | V step  L step")
+pv = pl = None
+for i, (J, k, a, b, c, d, e, f, g2, h) in enumerate(rows):
     if i % max(1, nb // 32) == 0:
-        step = e - prev if prev is not None else 0.0
-        print(f"{int(J):4d} {int(k):3d} {a:8.1f} {b:9.1f} {c:8.1f} {d:9.1f} {e:10.1f} | {b-a:5.1f} {c-b:8.2f} {d-c:7.2f} {e-d:6.2f} | {step:6.2f}")
-    prev = e
-ends = rows[:, 6]
-print(f"solve_us mean {np.mean(rows[:,6]-rows[:,5]):.2f}  near_us mean {np.mean(rows[:,5]-rows[:,4]):.2f}  "
-      f"sync+merge mean {np.mean(rows[:,4]-rows[:,3]):.2f}")
-print(f"chain per block (solve_done to solve_done): mean {np.mean(np.diff(ends)):.2f} median {np.median(np.diff(ends)):.2f} us;"
-      f" handoff (prev solve_done -> my solve start) mean {np.mean(rows[1:,5]-rows[:-1,6]):.2f} us")
+        sv = e - pv if pv is not None else 0.0
+        sl = h - pl if pl is not None else 0.0
+        print(f"{int(J):4d} {int(k):3d} {a:8.1f} {b:9.1f} | {c:8.1f} {d:9.1f} {e:10.1f} | {f:8.1f} {g2:9.1f} {h:10.1f} | {e-d:6.2f} {h-g2:7.2f} | {sv:6.2f} {sl:6.2f}")
+    pv, pl = e, h
+print(f"V: solve mean {np.mean(rows[:,6]-rows[:,5]):.2f} us, handoff (prev solve_done -> my solve start) mean {np.mean(rows[1:,5]-rows[:-1,6]):.2f}, "
+      f"chain step mean {np.mean(np.diff(rows[:,6])):.2f}")
+print(f"L: solve mean {np.mean(rows[:,9]-rows[:,8]):.2f} us, handoff mean {np.mean(rows[1:,8]-rows[:-1,9]):.2f}, "
+      f"chain step mean {np.mean(np.diff(rows[:,9])):.2f};  L setup(after sync) - far_done mean {np.mean(rows[:,7]-rows[:,3]):.2f}")
+print(f"L: prev L solve_done -> my far_done mean {np.mean(rows[1:,3]-rows[:-1,9]):.2f}; my far_done -> L setup done {np.mean(rows[:,7]-rows[:,3]):.2f}; "
+      f"L setup done -> near done {np.mean(rows[:,8]-rows[:,7]):.2f}")

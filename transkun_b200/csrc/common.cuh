@@ -46,6 +46,27 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, int 
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// variants taking a precomputed 32-bit shared-window address (no generic->shared conversion per call)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(unsigned saddr, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds64(unsigned saddr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -55,7 +55,9 @@ constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 32 * 4;
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
 constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 16;
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
-constexpr size_t kSweepSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + 2 * kTileFloats * 4;
+constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 16;  // untagged copy of the mailbox row: [V0..7 | L0..7]
+constexpr size_t kSweepSmem =
+    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
-    float *diagS = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);  // [NG][BX rows][BX cols]
+    float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
+    float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
     float *nearS = diagS + kTileFloats;                                             // [NG][BX rows][BX cols]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int nvalid = min(max(N - nq, 0), 4);
     float *my_ring = ring + (size_t)warp * kRingFloatsPerWarp + lane * 4;  // + slot*256 (+128 for column 1)
     unsigned long long *my_q = qring + (size_t)warp * kQWordsPerWarp;      // + slot*16 + {0..7 V, 8..15 L}
+    float *my_qc = qcomp + (size_t)warp * kQcFloatsPerWarp;
     float2 *my_partV = reinterpret_cast<float2 *>(ring + (size_t)warp * kRingFloatsPerWarp);  // [NG][BX]
     float2 *my_partL = my_partV + NG * BX;
     // lanes 0-3 fetch the Viterbi mailbox row (4 x 16 B), lanes 4-7 the log-sum row
@@ -201,96 +205,91 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int R = T - (x0 + 2 * BX);
         const int myrows = R > warp ? (R - warp + NW - 1) / NW : 0;
         if (myrows > 0) {
-            // running source pointers of the next row to issue (all 32 columns are valid here)
-            const float *sp0 = p.Sbase, *sp1 = p.Sbase;
-            if (nvalid > 0) {
-                sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - warp) * p.sy + nq;
-                sp1 = sp0 + p.sx;
-            }
+            // running source pointers of the next row to issue (all 32 columns are valid here); rows past
+            // the end are issued with src-size 0 (no global access), so the loop body has no branches
+            const float *sp0 = p.Sbase;
+            if (nvalid > 0) sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - warp) * p.sy + nq;
             const long long sstep = nvalid > 0 ? row_step : 0;
+            const long long scol = nvalid > 0 ? p.sx : 0;
             const unsigned long long *qp =
                 (lane < 4 ? mboxV : mboxL) + (size_t)(T - 1 - warp) * p.Npad + n0 + 2 * (lane & 3);
             const int nbytes = nvalid * 4;
+            const unsigned ring_s = smem_u32(my_ring);               // + slot*1024 (+512 for column 1)
+            const unsigned q_s = smem_u32(my_q);                     // + slot*128: tagged words
+            const unsigned qc_s = smem_u32(my_qc);                   // + slot*64 : 16 untagged values
             int ti = 0;  // next row to issue
             auto issue = [&]() {
-                float *dst = my_ring + (ti & (SLOTS - 1)) * 256;
+                const int live = ti < myrows;
+                const unsigned so = (unsigned)(ti & (SLOTS - 1));
                 if (A16) {
-                    cp_async16(dst, sp0, nbytes);
-                    cp_async16(dst + 128, sp1, nbytes);
+                    cp_async16_s(ring_s + so * 1024, sp0, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so * 1024 + 512, sp0 + scol, live ? nbytes : 0);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        cp_async4(dst + q, sp0 + (q < nvalid ? q : 0), q < nvalid ? 4 : 0);
-                        cp_async4(dst + 128 + q, sp1 + (q < nvalid ? q : 0), q < nvalid ? 4 : 0);
+                        const int nb4 = (live && q < nvalid) ? 4 : 0;
+                        cp_async4_s(ring_s + so * 1024 + q * 4, sp0 + (q < nvalid ? q : 0), nb4);
+                        cp_async4_s(ring_s + so * 1024 + 512 + q * 4, sp0 + scol + (q < nvalid ? q : 0), nb4);
                     }
                 }
-                if (qfetch) cp_async16(my_q + (ti & (SLOTS - 1)) * 16 + 2 * lane, qp, 16);
+                if (qfetch) cp_async16_s(q_s + so * 128 + lane * 16, qp, live ? 16 : 0);
                 sp0 -= sstep;
-                sp1 -= sstep;
                 qp -= q_step;
                 ++ti;
             };
 #pragma unroll
             for (int t = 0; t < D; ++t) {
-                if (t < myrows) issue();
+                issue();
                 cp_async_commit();
             }
             int y = T - 1 - warp;
-            for (int tb = 0; tb < myrows; tb += CH) {
-                float xl[CH][2][4];
+            // one row: wait for its S and mailbox words, validate the tags, distribute q, Viterbi update,
+            // and (log-sum) stage x = S*log2e + q for the chunk flush
+            auto do_row = [&](int t, float (&xl)[2][4]) {
+                issue();
+                cp_async_commit();
+                cp_async_wait<D>();
+                __syncwarp();
+                const unsigned so = (unsigned)(t & (SLOTS - 1));
+                unsigned long long word = 0;
+                if (lane < 16) word = lds64(q_s + so * 128 + lane * 8);
+                const bool ok = !qcheck || (unsigned)(word >> 32) == epoch;
+                if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
+                    if (!ok)
+                        word = poll_slow((lane < 8 ? mboxV : mboxL) + (size_t)y * p.Npad + n0 + (lane & 7), epoch,
+                                         p.status);
+                }
+                if (lane < 16) sts32(qc_s + so * 64 + lane * 4, __uint_as_float((unsigned)word));
+                __syncwarp();
+                float4 qv4, ql4;
+                if (DO_V) qv4 = lds128(qc_s + so * 64 + quad * 16);
+                if (DO_L) ql4 = lds128(qc_s + so * 64 + 32 + quad * 16);
+                float4 a[2];
+                a[0] = lds128(ring_s + so * 1024);
+                a[1] = lds128(ring_s + so * 1024 + 512);
+                const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
+                const float ql[4] = {ql4.x, ql4.y, ql4.z, ql4.w};
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const int t = tb + i;
-                    if (t < myrows) {  // warp-uniform
-                        if (ti < myrows) issue();
-                        cp_async_commit();
-                        cp_async_wait<D>();
-                        __syncwarp();
-                        const int slot = t & (SLOTS - 1);
-                        // -- q[y] of my tracks: lanes 0-7 hold the Viterbi words, 8-15 the log-sum words
-                        unsigned long long word = 0;
-                        if (lane < 16) word = my_q[slot * 16 + lane];
-                        const bool ok = !qcheck || (unsigned)(word >> 32) == epoch;
-                        if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
-                            if (!ok)
-                                word = poll_slow((lane < 8 ? mboxV : mboxL) + (size_t)y * p.Npad + n0 + (lane & 7),
-                                                 epoch, p.status);
+                for (int j = 0; j < 2; ++j) {
+                    const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (DO_V) {
+                            const float xv = qv[q] + av[q];
+                            const bool tk = (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
+                            vmax[j][q] = tk ? xv : vmax[j][q];
+                            vsel[j][q] = tk ? y : vsel[j][q];
                         }
-                        const float qval = __uint_as_float((unsigned)word);
-                        float qv[4], ql[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (DO_V) qv[q] = __shfl_sync(kFull, qval, quad * 4 + q);
-                            if (DO_L) ql[q] = __shfl_sync(kFull, qval, 8 + quad * 4 + q);
-                        }
-                        // -- S(y, my two columns, my four tracks)
-                        const float *slotp = my_ring + slot * 256;
-                        float4 a[2];
-                        a[0] = *reinterpret_cast<const float4 *>(slotp);
-                        a[1] = *reinterpret_cast<const float4 *>(slotp + 128);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (DO_V) {
-                                    const float xv = qv[q] + av[q];
-                                    const bool tk =
-                                        (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
-                                    vmax[j][q] = tk ? xv : vmax[j][q];
-                                    vsel[j][q] = tk ? y : vsel[j][q];
-                                }
-                                if (DO_L) xl[i][j][q] = fmaf(av[q], kLog2e, ql[q]);
-                            }
-                        }
-                        y -= NW;
-                    } else if (DO_L) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) xl[i][j][q] = -FLT_MAX;
+                        if (DO_L) xl[j][q] = fmaf(av[q], kLog2e, ql[q]);
                     }
                 }
+                y -= NW;
+            };
+            int t = 0;
+            for (; t + CH <= myrows; t += CH) {  // full chunks: one max/rescale per CH rows
+                float xl[CH][2][4];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) do_row(t + i, xl[i]);
                 if (DO_L) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
@@ -306,6 +305,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                             lS[j][q] = acc;
                             lM[j][q] = Mn;
                         }
+                }
+            }
+            for (; t < myrows; ++t) {  // at most CH-1 tail rows
+                float xl[2][4];
+                do_row(t, xl);
+                if (DO_L) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) lse_push(lM[j][q], lS[j][q], xl[j][q], 1.0f);
                 }
             }
         }
