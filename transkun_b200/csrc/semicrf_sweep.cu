@@ -43,7 +43,7 @@ constexpr int NG = 8;      // tracks per group
 constexpr int BX = 32;     // columns per block (= lanes of a solver warp)
 constexpr int NW = 16;     // warps per CTA: far field 16 row-slices; solve 8 tracks x 2 semirings
 constexpr int NT = NW * 32;
-constexpr int SLOTS = 8;   // per-warp FIFO depth (rows); SLOTS-1 rows in flight
+constexpr int SLOTS = 4;   // per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
 constexpr int CH = 4;      // rows per log-sum-exp rescale chunk
 constexpr int PB = 8;      // rows per publish batch
 
@@ -51,11 +51,11 @@ constexpr int PB = 8;      // rows per publish batch
 // diagonal block | near tile (block J+1 rows x block J columns), both transposed to [track][row][col].
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
-constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 32 * 4;
+constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
-constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 16;
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][track] tagged words
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
-constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 16;  // untagged copy of the mailbox row: [V0..7 | L0..7]
+constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
     kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
@@ -149,9 +149,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     float *my_qc = qcomp + (size_t)warp * kQcFloatsPerWarp;
     float2 *my_partV = reinterpret_cast<float2 *>(ring + (size_t)warp * kRingFloatsPerWarp);  // [NG][BX]
     float2 *my_partL = my_partV + NG * BX;
-    // lanes 0-3 fetch the Viterbi mailbox row (4 x 16 B), lanes 4-7 the log-sum row
-    const bool qfetch = (lane < 4 && DO_V) || (lane >= 4 && lane < 8 && DO_L);
-    const bool qcheck = (lane < 8 && DO_V) || (lane >= 8 && lane < 16 && DO_L);
     // solver mapping: warp -> (semiring, track), lane -> column
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
@@ -202,39 +199,55 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lM[j][q] = -FLT_MAX;
                 lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + 2 * BX);
-        const int myrows = R > warp ? (R - warp + NW - 1) / NW : 0;
-        if (myrows > 0) {
-            // running source pointers of the next row to issue (all 32 columns are valid here); rows past
+        const int R = T - (x0 + 2 * BX);          // far rows y = T-1 .. x0+2*BX, taken in adjacent pairs
+        const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
+        const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
+        if (mypairs > 0) {
+            // running source pointers of the next pair to issue (all 32 columns are valid here); pairs past
             // the end are issued with src-size 0 (no global access), so the loop body has no branches
             const float *sp0 = p.Sbase;
-            if (nvalid > 0) sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - warp) * p.sy + nq;
-            const long long sstep = nvalid > 0 ? row_step : 0;
+            if (nvalid > 0)
+                sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - 2 * warp) * p.sy + nq;
+            const long long sstep = nvalid > 0 ? 2 * row_step : 0;
             const long long scol = nvalid > 0 ? p.sx : 0;
+            const long long srow = nvalid > 0 ? p.sy : 0;
+            // mailbox fetch: lane = row*8 + kind*4 + track pair (lanes 0-15); tag check: lane = row*16 + kind*8 + track
+            const int f_row = lane >> 3, f_kind = (lane >> 2) & 1;
+            const bool qfetch = lane < 16 && (f_kind ? DO_L : DO_V);
             const unsigned long long *qp =
-                (lane < 4 ? mboxV : mboxL) + (size_t)(T - 1 - warp) * p.Npad + n0 + 2 * (lane & 3);
+                (f_kind ? mboxL : mboxV) + (size_t)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
+            const int c_row = lane >> 4, c_kind = (lane >> 3) & 1;
+            const bool c_need = c_kind ? DO_L : DO_V;
+            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + n0 + (lane & 7);  // + y * Npad
+            const float c_absent = c_kind ? -FLT_MAX : -INFINITY;  // q of a row that does not exist
             const int nbytes = nvalid * 4;
-            const unsigned ring_s = smem_u32(my_ring);               // + slot*1024 (+512 for column 1)
-            const unsigned q_s = smem_u32(my_q);                     // + slot*128: tagged words
-            const unsigned qc_s = smem_u32(my_qc);                   // + slot*64 : 16 untagged values
-            int ti = 0;  // next row to issue
+            const unsigned ring_s = smem_u32(my_ring);  // + slot*2048 + row*1024 + col*512
+            const unsigned q_s = smem_u32(my_q);        // + slot*256: tagged words [row][kind][track]
+            const unsigned qc_s = smem_u32(my_qc);      // + slot*128: untagged values [row][kind][track]
+            int ti = 0;  // next pair to issue
             auto issue = [&]() {
-                const int live = ti < myrows;
-                const unsigned so = (unsigned)(ti & (SLOTS - 1));
+                const int live = ti < mypairs;
+                const int liveB = live && (2 * (warp + ti * NW) + 1 < R);
+                const unsigned so = (unsigned)(ti & (SLOTS - 1)) * 2048u;
                 if (A16) {
-                    cp_async16_s(ring_s + so * 1024, sp0, live ? nbytes : 0);
-                    cp_async16_s(ring_s + so * 1024 + 512, sp0 + scol, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so, sp0, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 512, sp0 + scol, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 1024, sp0 - srow, liveB ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 1536, sp0 - srow + scol, liveB ? nbytes : 0);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int nb4 = (live && q < nvalid) ? 4 : 0;
-                        cp_async4_s(ring_s + so * 1024 + q * 4, sp0 + (q < nvalid ? q : 0), nb4);
-                        cp_async4_s(ring_s + so * 1024 + 512 + q * 4, sp0 + scol + (q < nvalid ? q : 0), nb4);
+                        const int qq = q < nvalid ? q : 0;
+                        const int nA = (live && q < nvalid) ? 4 : 0, nB = (liveB && q < nvalid) ? 4 : 0;
+                        cp_async4_s(ring_s + so + q * 4, sp0 + qq, nA);
+                        cp_async4_s(ring_s + so + 512 + q * 4, sp0 + scol + qq, nA);
+                        cp_async4_s(ring_s + so + 1024 + q * 4, sp0 - srow + qq, nB);
+                        cp_async4_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
                     }
                 }
-                if (qfetch) cp_async16_s(q_s + so * 128 + lane * 16, qp, live ? 16 : 0);
+                if (qfetch) cp_async16_s(q_s + (so >> 3) + lane * 16, qp, (f_row ? liveB : live) ? 16 : 0);
                 sp0 -= sstep;
-                qp -= q_step;
+                qp -= 2 * q_step;
                 ++ti;
             };
 #pragma unroll
@@ -242,54 +255,55 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 issue();
                 cp_async_commit();
             }
-            int y = T - 1 - warp;
-            // one row: wait for its S and mailbox words, validate the tags, distribute q, Viterbi update,
+            int yA = T - 1 - 2 * warp;
+            // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
             // and (log-sum) stage x = S*log2e + q for the chunk flush
-            auto do_row = [&](int t, float (&xl)[2][4]) {
+            auto do_pair = [&](int t, float (&xlA)[2][4], float (&xlB)[2][4]) {
                 issue();
                 cp_async_commit();
                 cp_async_wait<D>();
                 __syncwarp();
                 const unsigned so = (unsigned)(t & (SLOTS - 1));
-                unsigned long long word = 0;
-                if (lane < 16) word = lds64(q_s + so * 128 + lane * 8);
-                const bool ok = !qcheck || (unsigned)(word >> 32) == epoch;
+                const bool hasB = 2 * (warp + t * NW) + 1 < R;
+                unsigned long long word = lds64(q_s + so * 256 + lane * 8);
+                const bool need = c_need && (c_row == 0 || hasB);
+                const bool ok = !need || (unsigned)(word >> 32) == epoch;
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
-                    if (!ok)
-                        word = poll_slow((lane < 8 ? mboxV : mboxL) + (size_t)y * p.Npad + n0 + (lane & 7), epoch,
-                                         p.status);
+                    if (!ok) word = poll_slow(cq + (size_t)(yA - c_row) * p.Npad, epoch, p.status);
                 }
-                if (lane < 16) sts32(qc_s + so * 64 + lane * 4, __uint_as_float((unsigned)word));
+                sts32(qc_s + so * 128 + lane * 4, (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word));
                 __syncwarp();
-                float4 qv4, ql4;
-                if (DO_V) qv4 = lds128(qc_s + so * 64 + quad * 16);
-                if (DO_L) ql4 = lds128(qc_s + so * 64 + 32 + quad * 16);
-                float4 a[2];
-                a[0] = lds128(ring_s + so * 1024);
-                a[1] = lds128(ring_s + so * 1024 + 512);
-                const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
-                const float ql[4] = {ql4.x, ql4.y, ql4.z, ql4.w};
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+                for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
+                    float4 qv4, ql4;
+                    if (DO_V) qv4 = lds128(qc_s + so * 128 + rr * 64 + quad * 16);
+                    if (DO_L) ql4 = lds128(qc_s + so * 128 + rr * 64 + 32 + quad * 16);
+                    const float4 a0 = lds128(ring_s + so * 2048 + rr * 1024);
+                    const float4 a1 = lds128(ring_s + so * 2048 + rr * 1024 + 512);
+                    const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
+                    const float ql[4] = {ql4.x, ql4.y, ql4.z, ql4.w};
+                    const float av[2][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}};
+                    const int y = yA - rr;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (DO_V) {
-                            const float xv = qv[q] + av[q];
-                            const bool tk = (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
-                            vmax[j][q] = tk ? xv : vmax[j][q];
-                            vsel[j][q] = tk ? y : vsel[j][q];
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (DO_V) {
+                                const float xv = qv[q] + av[j][q];
+                                const bool tk = (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
+                                vmax[j][q] = tk ? xv : vmax[j][q];
+                                vsel[j][q] = tk ? y : vsel[j][q];
+                            }
+                            if (DO_L) (rr ? xlB : xlA)[j][q] = fmaf(av[j][q], kLog2e, ql[q]);
                         }
-                        if (DO_L) xl[j][q] = fmaf(av[q], kLog2e, ql[q]);
-                    }
                 }
-                y -= NW;
+                yA -= 2 * NW;
             };
             int t = 0;
-            for (; t + CH <= myrows; t += CH) {  // full chunks: one max/rescale per CH rows
+            for (; t + 2 <= mypairs; t += 2) {  // full chunks: one max/rescale per CH = 4 rows
                 float xl[CH][2][4];
-#pragma unroll
-                for (int i = 0; i < CH; ++i) do_row(t + i, xl[i]);
+                do_pair(t, xl[0], xl[1]);
+                do_pair(t + 1, xl[2], xl[3]);
                 if (DO_L) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
@@ -307,14 +321,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         }
                 }
             }
-            for (; t < myrows; ++t) {  // at most CH-1 tail rows
-                float xl[2][4];
-                do_row(t, xl);
+            if (t < mypairs) {  // one tail pair
+                float xl[2][2][4];
+                do_pair(t, xl[0], xl[1]);
                 if (DO_L) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) lse_push(lM[j][q], lS[j][q], xl[j][q], 1.0f);
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) lse_push(lM[j][q], lS[j][q], xl[i][j][q], 1.0f);
                 }
             }
         }
