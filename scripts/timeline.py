@@ -21,14 +21,16 @@ L = _lib.load()
 score, noise = make_inputs("randn", T, N, 1234)
 s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
 grid_max = 148
-tl = torch.zeros((grid_max, 64, 8), dtype=torch.int64, device="cuda")
+tl = torch.zeros((grid_max * 64 * 8 + grid_max * 64 * 16 * 8,), dtype=torch.int64, device="cuda")
 L.tkb_debug_set_timeline.argtypes = [ctypes.c_void_p]
 L.tkb_debug_set_timeline(tl.data_ptr())
 for _ in range(3):
     tl.zero_()
     sweep(s, z, BACKWARD, flags)
     torch.cuda.synchronize()
-t = tl.cpu().numpy().astype(np.float64)
+tall = tl.cpu().numpy().astype(np.float64)
+t = tall[: grid_max * 64 * 8].reshape(grid_max, 64, 8)
+wt = tall[grid_max * 64 * 8:].reshape(grid_max, 64, 16, 8)
 G = (N + 7) // 8
 nb = (T + 31) // 32
 K = min(148 // G, nb)
@@ -56,3 +58,19 @@ print(f"L: solve mean {np.mean(rows[:,9]-rows[:,8]):.2f} us, handoff mean {np.me
       f"chain step mean {np.mean(np.diff(rows[:,9])):.2f};  L setup(after sync) - far_done mean {np.mean(rows[:,7]-rows[:,3]):.2f}")
 print(f"L: prev L solve_done -> my far_done mean {np.mean(rows[1:,3]-rows[:-1,9]):.2f}; my far_done -> L setup done {np.mean(rows[:,7]-rows[:,3]):.2f}; "
       f"L setup done -> near done {np.mean(rows[:,8]-rows[:,7]):.2f}")
+
+# per-warp stamps for a few mid-run blocks of group 0:
+# 0 far loop done | 1 partials written | 2 after __syncthreads | 3 setup done | 4 near tile done | 5 solve done
+print("\nper-warp stamps relative to the PREVIOUS block's latest solve_done (us); warps 0-7 Viterbi, 8-15 log-sum")
+for J in (40, 39, 20, 8):
+    if J + 1 > nb - 1:
+        continue
+    k, idx = (nb - 1 - J) % K, (nb - 1 - J) // K
+    kp, idxp = (nb - 1 - (J + 1)) % K, (nb - 1 - (J + 1)) // K
+    kpp, idxpp = (nb - 1 - (J + 2)) % K, (nb - 1 - (J + 2)) // K
+    ref = wt[kp, idxp, :, 5].max()
+    refV, refL = wt[kp, idxp, :8, 5].max(), wt[kp, idxp, 8:, 5].max()
+    print(f"block J={J}: prev block solve_done V {0.0:.2f} L {(refL - refV) / 1e3:.2f} (rel. to prev V done); "
+          f"block J+2 solve_done V {(wt[kpp, idxpp, :8, 5].max() - refV) / 1e3:.2f} L {(wt[kpp, idxpp, 8:, 5].max() - refV) / 1e3:.2f}")
+    for w in range(16):
+        print(f"  warp {w:2d}: " + " ".join(f"{(wt[k, idx, w, sidx] - refV) / 1e3:8.2f}" for sidx in range(6)))

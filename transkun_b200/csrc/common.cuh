@@ -85,7 +85,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
 

@@ -104,9 +104,19 @@ __device__ __forceinline__ void publish(unsigned long long *w, float val, unsign
         if (threadIdx.x == 0 && p.timeline && owned_idx < 64)                                               \
             p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + (slot)] = globaltimer_ns(); \
     } while (0)
+// per-warp stamps: timeline + 148*64*8 words, laid out [grid][64][NW][8]
+#define TKB_WSTAMP(slot)                                                                                        \
+    do {                                                                                                        \
+        if (lane == 0 && p.timeline && owned_idx < 64)                                                          \
+            p.timeline[(size_t)148 * 64 * 8 + (((size_t)blockIdx.x * 64 + owned_idx) * NW + warp) * 8 + (slot)] = \
+                globaltimer_ns();                                                                               \
+    } while (0)
 #else
 #define TKB_STAMP(slot) \
     do {                \
+    } while (0)
+#define TKB_WSTAMP(slot) \
+    do {                 \
     } while (0)
 #endif
 
@@ -334,6 +344,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 }
             }
         }
+        TKB_WSTAMP(0);
         // ---- B. hand the 16 partials to the solver mapping (via this warp's drained FIFO) --------
         cp_async_wait_all();
         __syncwarp();
@@ -346,7 +357,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 if (DO_L) my_partL[o] = make_float2(lM[j][q], lS[j][q]);
             }
         TKB_STAMP(1);
+        TKB_WSTAMP(1);
         __syncthreads();
+        TKB_WSTAMP(2);
 
         const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
         const bool active = x < T;
@@ -381,12 +394,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (x == T - 1) best = -0.0f;
             const float eta_top = (c == BX - 1 && nr > 0) ? s_eta : -INFINITY;  // skip from row x0+BX
             TKB_STAMP(2);
+            TKB_WSTAMP(3);
             // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX ------------------------------------------
             if (nr > 0) {
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    // wait only for the rows of this batch ...
                     if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
+                    // ... and re-request every still-stale word of the later batches NOW, so that the round
+                    // trip overlaps this batch's pushes instead of following them
+                    if ((lane >> 3) < b && (unsigned)(word >> 32) != epoch) word = ld_relaxed_u64(wrow);
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
@@ -403,6 +421,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 best = fmaxf(best, xk);
             }
             TKB_STAMP(3);
+            TKB_WSTAMP(4);
             // ---- D. diagonal solve: value chain = FADD -> SHFL -> FADD -> FMNMX ------------------
             float qmine = 0.0f;
 #pragma unroll
@@ -423,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             qmine = (c == 0) ? best + dr : qmine;
             if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
             TKB_STAMP(4);
+            TKB_WSTAMP(5);
             if (active && s_nok) {
                 const int osel = bsel < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel : T - 1 - bsel);
                 p.code[(size_t)(n0 + sn) * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
@@ -469,12 +489,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
                 p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 5] = globaltimer_ns();
 #endif
+            TKB_WSTAMP(3);
             // ---- C. near tile -----------------------------------------------------------------------
             if (nr > 0) {
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    // wait only for the rows of this batch ...
                     if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
+                    // ... and re-request every still-stale word of the later batches NOW, so that the round
+                    // trip overlaps this batch's pushes instead of following them
+                    if ((lane >> 3) < b && (unsigned)(word >> 32) != epoch) word = ld_relaxed_u64(wrow);
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
@@ -488,6 +513,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
                 p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 6] = globaltimer_ns();
 #endif
+            TKB_WSTAMP(4);
             // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
 #pragma unroll
             for (int e = BX - 1; e >= 1; --e) {
@@ -509,6 +535,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
                 p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 7] = globaltimer_ns();
 #endif
+            TKB_WSTAMP(5);
         }
         __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
     }
