@@ -44,7 +44,7 @@ constexpr int BX = 32;     // columns per block (= lanes of a solver warp)
 constexpr int NW = 16;     // warps per CTA: far field 16 row-slices; solve 8 tracks x 2 semirings
 constexpr int NT = NW * 32;
 constexpr int SLOTS = 4;   // per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
-constexpr int CH = 4;      // rows per log-sum-exp rescale chunk
+constexpr int CH = 2;      // rows per log-sum-exp rescale chunk (= one row pair)
 constexpr int PB = 8;      // rows per publish batch
 
 // shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
@@ -57,7 +57,8 @@ constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][trac
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
-    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4;
+    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
+    2 * NT * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -111,7 +112,17 @@ __device__ __forceinline__ void publish(unsigned long long *w, float val, unsign
             p.timeline[(size_t)148 * 64 * 8 + (((size_t)blockIdx.x * 64 + owned_idx) * NW + warp) * 8 + (slot)] = \
                 globaltimer_ns();                                                                               \
     } while (0)
+// stamp that cannot be taken before `dep` (a register value) is available
+#define TKB_WSTAMP_DEP(slot, dep)                                                                               \
+    do {                                                                                                        \
+        if (lane == 0 && p.timeline && owned_idx < 64)                                                          \
+            p.timeline[(size_t)148 * 64 * 8 + (((size_t)blockIdx.x * 64 + owned_idx) * NW + warp) * 8 + (slot)] = \
+                globaltimer_ns() + ((__float_as_uint(dep) == 0x7fedcba9u) ? 1ull : 0ull);                       \
+    } while (0)
 #else
+#define TKB_WSTAMP_DEP(slot, dep) \
+    do {                          \
+    } while (0)
 #define TKB_STAMP(slot) \
     do {                \
     } while (0)
@@ -140,6 +151,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
     float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
     float *nearS = diagS + kTileFloats;                                             // [NG][BX rows][BX cols]
+    float *park = nearS + kTileFloats;                                              // [2][NT] per-thread constants
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -191,10 +203,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         // unary + skip weights of my solver column (kept in registers across the far field)
         const int c = lane;
         const int x = x0 + c;
-        float s_d = 0.0f, s_eta = 0.0f;
-        if (x < T && s_nok) {
-            s_d = __ldg(p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn);
-            if (x < T - 1) s_eta = __ldg(p.etabase + (long long)x * p.se + n0 + sn);
+        // (parked in shared memory while the far field needs every register: a compiler spill would be
+        // re-read from L2 on the critical path, L1 being almost entirely carved out as shared memory)
+        {
+            float d0 = 0.0f, e0 = 0.0f;
+            if (x < T && s_nok) {
+                d0 = __ldg(p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn);
+                if (x < T - 1) e0 = __ldg(p.etabase + (long long)x * p.se + n0 + sn);
+            }
+            park[threadIdx.x] = d0;
+            park[NT + threadIdx.x] = e0;
         }
 
         // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th --------------
@@ -309,38 +327,22 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 }
                 yA -= 2 * NW;
             };
-            int t = 0;
-            for (; t + 2 <= mypairs; t += 2) {  // full chunks: one max/rescale per CH = 4 rows
+            for (int t = 0; t < mypairs; ++t) {  // one max/rescale per pair of rows
                 float xl[CH][2][4];
                 do_pair(t, xl[0], xl[1]);
-                do_pair(t + 1, xl[2], xl[3]);
                 if (DO_L) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            float m = xl[0][j][q];
-#pragma unroll
-                            for (int i = 1; i < CH; ++i) m = fmaxf(m, xl[i][j][q]);
+                            const float m = fmaxf(xl[0][j][q], xl[1][j][q]);
                             const float Mn = fmaxf(lM[j][q], m);
                             float acc = lS[j][q] * ex2f(lM[j][q] - Mn);
-#pragma unroll
-                            for (int i = 0; i < CH; ++i) acc += ex2f(xl[i][j][q] - Mn);
+                            acc += ex2f(xl[0][j][q] - Mn);
+                            acc += ex2f(xl[1][j][q] - Mn);
                             lS[j][q] = acc;
                             lM[j][q] = Mn;
                         }
-                }
-            }
-            if (t < mypairs) {  // one tail pair
-                float xl[2][2][4];
-                do_pair(t, xl[0], xl[1]);
-                if (DO_L) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) lse_push(lM[j][q], lS[j][q], xl[i][j][q], 1.0f);
                 }
             }
         }
@@ -359,10 +361,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         TKB_STAMP(1);
         TKB_WSTAMP(1);
         __syncthreads();
-        TKB_WSTAMP(2);
 
         const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
         const bool active = x < T;
+        const float s_d = park[threadIdx.x], s_eta = park[NT + threadIdx.x];
         // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows
         // or columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
         // near-tile mailbox words: lane i fetches row i (one round trip for everything already published)
@@ -386,9 +388,11 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                     bsel = sl;
                 }
             }
+            TKB_WSTAMP_DEP(2, best);
             float sreg[BX];
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
+            TKB_WSTAMP_DEP(6, sreg[BX - 1] + sreg[1]);
             const float dr = relu_mask(s_d);
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
             if (x == T - 1) best = -0.0f;
@@ -464,8 +468,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
             }
+            TKB_WSTAMP_DEP(2, S);
             const float sp2 = softplus_ref(s_d) * kLog2e;
             const float eta2 = s_eta * kLog2e;
+            TKB_WSTAMP_DEP(6, sp2);
             float sreg[BX];
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
