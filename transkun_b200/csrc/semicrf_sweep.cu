@@ -206,14 +206,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         // (parked in shared memory while the far field needs every register: a compiler spill would be
         // re-read from L2 on the critical path, L1 being almost entirely carved out as shared memory)
         {
-            float d0 = 0.0f, e0 = 0.0f;
-            if (x < T && s_nok) {
-                d0 = __ldg(p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn);
-                if (x < T - 1) e0 = __ldg(p.etabase + (long long)x * p.se + n0 + sn);
-            }
-            park[threadIdx.x] = d0;
-            park[NT + threadIdx.x] = e0;
+            const bool has_d = x < T && s_nok, has_e = has_d && x < T - 1;
+            cp_async4(&park[threadIdx.x], has_d ? p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn : p.Sbase,
+                      has_d ? 4 : 0);
+            cp_async4(&park[NT + threadIdx.x], has_e ? p.etabase + (long long)x * p.se + n0 + sn : p.Sbase,
+                      has_e ? 4 : 0);
         }
+        cp_async_commit();
 
         // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th --------------
         float vmax[2][4], lM[2][4], lS[2][4];
@@ -368,10 +367,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows
         // or columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
         // near-tile mailbox words: lane i fetches row i (one round trip for everything already published)
+        // They are fetched with cp.async (16 B = my track's word and its neighbour's) into this warp's drained
+        // mailbox FIFO: a register-destination load in flight here would share a scoreboard slot with the
+        // shared-memory loads of the setup below and make each of them wait a full L2 round trip.
         unsigned long long word = 0;
         const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
         const bool solver_on = s_is_lse ? DO_L : DO_V;
-        if (solver_on && lane < nr) word = ld_relaxed_u64(wrow);
+        const unsigned nq_s = smem_u32(my_q) + lane * 16;
+        const unsigned nq_mine = nq_s + (sn & 1) * 8;
+        const unsigned long long *wrow16 = wrow - (sn & 1);
+        if (solver_on) cp_async16_s(nq_s, wrow16, lane < nr ? 16 : 0);
+        cp_async_commit();
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
             float best = -INFINITY;
@@ -401,14 +407,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             TKB_WSTAMP(3);
             // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX ------------------------------------------
             if (nr > 0) {
+                cp_async_wait_all();
+                word = lds64(nq_mine);
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    // wait only for the rows of this batch ...
+                    // wait only for the rows of this batch (nothing else to do: poll with plain loads) ...
                     if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
-                    // ... and re-request every still-stale word of the later batches NOW, so that the round
-                    // trip overlaps this batch's pushes instead of following them
-                    if ((lane >> 3) < b && (unsigned)(word >> 32) != epoch) word = ld_relaxed_u64(wrow);
+                    // ... and re-request every still-stale word of the later batches NOW (asynchronously), so
+                    // that the round trip overlaps this batch's pushes instead of following them
+                    const bool refresh = (lane >> 3) < b && (unsigned)(word >> 32) != epoch;
+                    if (refresh) cp_async16_s(nq_s, wrow16, 16);
+                    cp_async_commit();
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
@@ -418,6 +428,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         bsel = tk ? x0 + BX + r : bsel;
                         best = fmaxf(best, xi);
                     }
+                    cp_async_wait_all();
+                    if (refresh) word = lds64(nq_mine);
                 }
                 // the skip out of the top column: candidate 0 of the reference, so it wins every tie
                 const float xk = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top;
@@ -498,20 +510,26 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             TKB_WSTAMP(3);
             // ---- C. near tile -----------------------------------------------------------------------
             if (nr > 0) {
+                cp_async_wait_all();
+                word = lds64(nq_mine);
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    // wait only for the rows of this batch ...
+                    // wait only for the rows of this batch (nothing else to do: poll with plain loads) ...
                     if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
-                    // ... and re-request every still-stale word of the later batches NOW, so that the round
-                    // trip overlaps this batch's pushes instead of following them
-                    if ((lane >> 3) < b && (unsigned)(word >> 32) != epoch) word = ld_relaxed_u64(wrow);
+                    // ... and re-request every still-stale word of the later batches NOW (asynchronously), so
+                    // that the round trip overlaps this batch's pushes instead of following them
+                    const bool refresh = (lane >> 3) < b && (unsigned)(word >> 32) != epoch;
+                    if (refresh) cp_async16_s(nq_s, wrow16, 16);
+                    cp_async_commit();
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
                         const float vb = __shfl_sync(kFull, val, r);
                         lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);
                     }
+                    cp_async_wait_all();
+                    if (refresh) word = lds64(nq_mine);
                 }
                 lse_push(M, S, __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top, 1.0f);
             }
