@@ -409,16 +409,29 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (nr > 0) {
                 cp_async_wait_all();
                 word = lds64(nq_mine);
+                bool pending = false, mine_pending = false;  // an asynchronous refresh of stale words is in flight
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    // wait only for the rows of this batch (nothing else to do: poll with plain loads) ...
-                    if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                    const unsigned bm = 0xffu << (PB * b);
+                    unsigned stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
+                    if (pending && (stale & bm)) {  // this batch needs the refreshed words: collect them now
+                        cp_async_wait_all();
+                        if (mine_pending) word = lds64(nq_mine);
+                        pending = mine_pending = false;
+                        stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
+                    }
+                    // still not published: nothing else to do, poll with plain loads
+                    if ((stale & bm) && (lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
-                    // ... and re-request every still-stale word of the later batches NOW (asynchronously), so
-                    // that the round trip overlaps this batch's pushes instead of following them
-                    const bool refresh = (lane >> 3) < b && (unsigned)(word >> 32) != epoch;
-                    if (refresh) cp_async16_s(nq_s, wrow16, 16);
-                    cp_async_commit();
+                    // re-request the stale words of the later batches asynchronously: the round trip overlaps
+                    // the pushes below
+                    const unsigned later = stale & ~(0xffffffffu << (PB * b));
+                    if (!pending && later) {
+                        mine_pending = (later >> lane) & 1u;
+                        if (mine_pending) cp_async16_s(nq_s, wrow16, 16);
+                        cp_async_commit();
+                        pending = true;
+                    }
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
@@ -428,9 +441,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         bsel = tk ? x0 + BX + r : bsel;
                         best = fmaxf(best, xi);
                     }
-                    cp_async_wait_all();
-                    if (refresh) word = lds64(nq_mine);
                 }
+                cp_async_wait_all();  // drain before the FIFO is reused
                 // the skip out of the top column: candidate 0 of the reference, so it wins every tie
                 const float xk = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top;
                 bsel = (xk >= best) ? -1 : bsel;
@@ -512,25 +524,37 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             if (nr > 0) {
                 cp_async_wait_all();
                 word = lds64(nq_mine);
+                bool pending = false, mine_pending = false;  // an asynchronous refresh of stale words is in flight
                 for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    // wait only for the rows of this batch (nothing else to do: poll with plain loads) ...
-                    if ((lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
+                    const unsigned bm = 0xffu << (PB * b);
+                    unsigned stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
+                    if (pending && (stale & bm)) {  // this batch needs the refreshed words: collect them now
+                        cp_async_wait_all();
+                        if (mine_pending) word = lds64(nq_mine);
+                        pending = mine_pending = false;
+                        stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
+                    }
+                    // still not published: nothing else to do, poll with plain loads
+                    if ((stale & bm) && (lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
                         word = poll_slow(wrow, epoch, p.status);
                     const float val = __uint_as_float((unsigned)word);
-                    // ... and re-request every still-stale word of the later batches NOW (asynchronously), so
-                    // that the round trip overlaps this batch's pushes instead of following them
-                    const bool refresh = (lane >> 3) < b && (unsigned)(word >> 32) != epoch;
-                    if (refresh) cp_async16_s(nq_s, wrow16, 16);
-                    cp_async_commit();
+                    // re-request the stale words of the later batches asynchronously: the round trip overlaps
+                    // the pushes below
+                    const unsigned later = stale & ~(0xffffffffu << (PB * b));
+                    if (!pending && later) {
+                        mine_pending = (later >> lane) & 1u;
+                        if (mine_pending) cp_async16_s(nq_s, wrow16, 16);
+                        cp_async_commit();
+                        pending = true;
+                    }
 #pragma unroll
                     for (int i = PB - 1; i >= 0; --i) {
                         const int r = b * PB + i;
                         const float vb = __shfl_sync(kFull, val, r);
                         lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);
                     }
-                    cp_async_wait_all();
-                    if (refresh) word = lds64(nq_mine);
                 }
+                cp_async_wait_all();  // drain before the FIFO is reused
                 lse_push(M, S, __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top, 1.0f);
             }
 #ifdef TKB_TIMELINE
