@@ -18,19 +18,17 @@
 //   * tracks are independent -> groups of NG=8 tracks (one 32-byte sector of the
 //     track-innermost layout) form independent pipelines;
 //   * per group, K CTAs own the 32-column blocks round-robin (block J -> CTA
-//     (nb-1-J) mod K).  For its block J a CTA runs four phases:
-//       A  FAR FIELD: all rows y in blocks >= J+2 (order-free semiring mat-vec, the
-//          bulk of the bytes): 16 warps each own every 16th row, cp.async-staged into
-//          per-lane shared-memory FIFOs together with the mailbox row, accumulators
-//          in registers;
+//     (nb-1-J) mod K).  For its block J a CTA runs three phases:
+//       A  FAR FIELD: all rows y in later blocks (order-free semiring mat-vec, the bulk
+//          of the bytes): 16 warps each own every 16th PAIR of adjacent rows,
+//          cp.async-staged into per-lane shared-memory FIFOs together with the
+//          mailbox rows, accumulators in registers;
 //       B  the 16 partials are merged into the solver mapping: one warp per
 //          (track, semiring), lane = column;
-//       C  NEAR TILE: the 32 rows of block J+1 are consumed by the solver warps
-//          directly, in batches of 8 as the previous owner publishes them;
-//       D  DIAGONAL SOLVE: 31 dependent steps, one shuffle each.  The log-sum chain
-//          carries (M, S) pairs (value = M + log2 S) so no log sits on the chain, the
-//          skip weight is folded into the coefficient of the row right above a
-//          column, and rows are published in batches of 8 (one lg2 per batch);
+//       D  DIAGONAL SOLVE: 31 dependent steps, one shuffle each, branch-free.  The
+//          log-sum chain carries (M, S) pairs (value = M + log2 S) so no log sits on
+//          the chain, the skip weight is folded into the coefficient of the row right
+//          above a column, and rows are published in batches of 8 (one lg2 per batch);
 //   * solved rows are broadcast to the other CTAs of the group through a
 //     global-memory mailbox of 64-bit words {fp32 value, epoch tag}: one relaxed
 //     store publishes, one relaxed load observes (no fence, no flag, no reset).
@@ -48,7 +46,7 @@ constexpr int CH = 2;      // rows per log-sum-exp rescale chunk (= one row pair
 constexpr int PB = 8;      // rows per publish batch
 
 // shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
-// diagonal block | near tile (block J+1 rows x block J columns), both transposed to [track][row][col].
+// diagonal block transposed to [track][row][col] | parked per-thread constants | q of the row above the block.
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
@@ -57,8 +55,8 @@ constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][trac
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
-    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
-    2 * NT * 4;
+    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + kTileFloats * 4 +
+    2 * NT * 4 + 2 * NG * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -81,12 +79,16 @@ struct SweepParams {
 // Wait until the mailbox word carries this launch's epoch.  A protocol bug (or a
 // non-co-resident grid) must not hang the GPU: after ~4 s the wait gives up,
 // flags the workspace and lets the kernel drain with garbage.
+// BACKOFF_NS > 0 is for waits that are NOT on the critical path (far-field rows): hundreds of warps spinning
+// on the few mailbox lines the chain is currently writing slow the chain's own reader and writer down.
+template <int BACKOFF_NS>
 __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w, unsigned epoch, int *status) {
     unsigned long long t0 = globaltimer_ns();
     for (;;) {
         for (int i = 0; i < 64; ++i) {
             unsigned long long v = ld_relaxed_u64(w);
             if ((unsigned)(v >> 32) == epoch) return v;
+            if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
         }
         if (*(volatile int *)status != 0) return 0;
         if (globaltimer_ns() - t0 > 4000000000ull) {
@@ -95,6 +97,9 @@ __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w
         }
     }
 }
+#ifndef TKB_FAR_BACKOFF_NS
+#define TKB_FAR_BACKOFF_NS 400
+#endif
 __device__ __forceinline__ void publish(unsigned long long *w, float val, unsigned epoch) {
     st_relaxed_u64(w, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val));
 }
@@ -143,15 +148,20 @@ template <int DIR, bool A16, int MODE>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
     constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
+#ifdef TKB_PREFETCH_D
+    constexpr int D = TKB_PREFETCH_D;  // tuning builds
+#else
     constexpr int D = SLOTS - 1;
+#endif
+    static_assert(D >= 1 && D <= SLOTS - 1, "prefetch distance must leave one FIFO slot free");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
     float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
-    float *nearS = diagS + kTileFloats;                                             // [NG][BX rows][BX cols]
-    float *park = nearS + kTileFloats;                                              // [2][NT] per-thread constants
+    float *park = diagS + kTileFloats;                                              // [2][NT] per-thread constants
+    float *qtop = park + 2 * NT;                                                    // [2][NG] q of row x0+BX
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -186,18 +196,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of the near tile (block J+1)
         TKB_STAMP(0);
 
-        // ---- 0. prefetch the diagonal block and the near tile, transposed to [track][row][col];
-        //         rows beyond T (only in the last one or two blocks) are filled with -inf = "no candidate"
+        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
+        //         last block) are filled with -inf = "no candidate"
         for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
             const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
-            const bool nok = (n0 + n) < N;
-            const float *src = p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
             if (r > cc) {
-                if (r < ncols && nok) cp_async4(&diagS[(n * BX + r) * BX + cc], src, 4);
-                else diagS[(n * BX + r) * BX + cc] = -INFINITY;
+                if (r < ncols && (n0 + n) < N)
+                    cp_async4(&diagS[(n * BX + r) * BX + cc],
+                              p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
+                else
+                    diagS[(n * BX + r) * BX + cc] = -INFINITY;
             }
-            if (r < nr && nok) cp_async4(&nearS[(n * BX + r) * BX + cc], src + (long long)BX * p.sy, 4);
-            else if (nr > 0) nearS[(n * BX + r) * BX + cc] = -INFINITY;
         }
         cp_async_commit();
         // unary + skip weights of my solver column (kept in registers across the far field)
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         }
         cp_async_commit();
 
-        // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th --------------
+        // ---- A. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th pair ------------
         float vmax[2][4], lM[2][4], lS[2][4];
         int vsel[2][4];
 #pragma unroll
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lM[j][q] = -FLT_MAX;
                 lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + 2 * BX);          // far rows y = T-1 .. x0+2*BX, taken in adjacent pairs
+        const int R = T - (x0 + BX);              // rows y = T-1 .. x0+BX, taken in adjacent pairs
         const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
         const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
         if (mypairs > 0) {
@@ -296,9 +305,15 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 const bool need = c_need && (c_row == 0 || hasB);
                 const bool ok = !need || (unsigned)(word >> 32) == epoch;
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
-                    if (!ok) word = poll_slow(cq + (size_t)(yA - c_row) * p.Npad, epoch, p.status);
+                    if (!ok) {
+                        const unsigned long long *w = cq + (size_t)(yA - c_row) * p.Npad;
+                        word = (yA < x0 + 3 * BX) ? poll_slow<0>(w, epoch, p.status)
+                                                  : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
+                    }
                 }
-                sts32(qc_s + so * 128 + lane * 4, (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word));
+                const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
+                sts32(qc_s + so * 128 + lane * 4, qrow);
+                if (yA - c_row == x0 + BX) qtop[lane & 15] = qrow;  // [kind][track] of row x0+BX
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
@@ -366,18 +381,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const float s_d = park[threadIdx.x], s_eta = park[NT + threadIdx.x];
         // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows
         // or columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
-        // near-tile mailbox words: lane i fetches row i (one round trip for everything already published)
-        // They are fetched with cp.async (16 B = my track's word and its neighbour's) into this warp's drained
-        // mailbox FIFO: a register-destination load in flight here would share a scoreboard slot with the
-        // shared-memory loads of the setup below and make each of them wait a full L2 round trip.
-        unsigned long long word = 0;
-        const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
-        const bool solver_on = s_is_lse ? DO_L : DO_V;
-        const unsigned nq_s = smem_u32(my_q) + lane * 16;
-        const unsigned nq_mine = nq_s + (sn & 1) * 8;
-        const unsigned long long *wrow16 = wrow - (sn & 1);
-        if (solver_on) cp_async16_s(nq_s, wrow16, lane < nr ? 16 : 0);
-        cp_async_commit();
+        const bool has_next = nr > 0;  // a later block exists: the top column can skip into row x0+BX
+        const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
             float best = -INFINITY;
@@ -394,57 +399,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                     bsel = sl;
                 }
             }
-            TKB_WSTAMP_DEP(2, best);
             float sreg[BX];
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
-            TKB_WSTAMP_DEP(6, sreg[BX - 1] + sreg[1]);
             const float dr = relu_mask(s_d);
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
             if (x == T - 1) best = -0.0f;
-            const float eta_top = (c == BX - 1 && nr > 0) ? s_eta : -INFINITY;  // skip from row x0+BX
             TKB_STAMP(2);
             TKB_WSTAMP(3);
-            // ---- C. near tile: rows y = x0+BX+nr-1 .. x0+BX ------------------------------------------
-            if (nr > 0) {
-                cp_async_wait_all();
-                word = lds64(nq_mine);
-                bool pending = false, mine_pending = false;  // an asynchronous refresh of stale words is in flight
-                for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    const unsigned bm = 0xffu << (PB * b);
-                    unsigned stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
-                    if (pending && (stale & bm)) {  // this batch needs the refreshed words: collect them now
-                        cp_async_wait_all();
-                        if (mine_pending) word = lds64(nq_mine);
-                        pending = mine_pending = false;
-                        stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
-                    }
-                    // still not published: nothing else to do, poll with plain loads
-                    if ((stale & bm) && (lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
-                        word = poll_slow(wrow, epoch, p.status);
-                    const float val = __uint_as_float((unsigned)word);
-                    // re-request the stale words of the later batches asynchronously: the round trip overlaps
-                    // the pushes below
-                    const unsigned later = stale & ~(0xffffffffu << (PB * b));
-                    if (!pending && later) {
-                        mine_pending = (later >> lane) & 1u;
-                        if (mine_pending) cp_async16_s(nq_s, wrow16, 16);
-                        cp_async_commit();
-                        pending = true;
-                    }
-#pragma unroll
-                    for (int i = PB - 1; i >= 0; --i) {
-                        const int r = b * PB + i;
-                        const float qb = __shfl_sync(kFull, val, r);
-                        const float xi = qb + nearS[(sn * BX + r) * BX + c];
-                        const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
-                        bsel = tk ? x0 + BX + r : bsel;
-                        best = fmaxf(best, xi);
-                    }
-                }
-                cp_async_wait_all();  // drain before the FIFO is reused
-                // the skip out of the top column: candidate 0 of the reference, so it wins every tie
-                const float xk = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top;
+            // the skip out of the top column: candidate 0 of the reference, so it wins every tie
+            if (has_next && c == BX - 1) {
+                const float xk = qnext + s_eta;
                 bsel = (xk >= best) ? -1 : bsel;
                 best = fmaxf(best, xk);
             }
@@ -492,10 +457,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
             }
-            TKB_WSTAMP_DEP(2, S);
             const float sp2 = softplus_ref(s_d) * kLog2e;
             const float eta2 = s_eta * kLog2e;
-            TKB_WSTAMP_DEP(6, sp2);
             float sreg[BX];
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
@@ -514,49 +477,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 M = 0.0f;
                 S = 1.0f;
             }
-            const float eta_top = (c == BX - 1 && nr > 0) ? eta2 : -INFINITY;
 #ifdef TKB_TIMELINE
             if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
                 p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 5] = globaltimer_ns();
 #endif
             TKB_WSTAMP(3);
-            // ---- C. near tile -----------------------------------------------------------------------
-            if (nr > 0) {
-                cp_async_wait_all();
-                word = lds64(nq_mine);
-                bool pending = false, mine_pending = false;  // an asynchronous refresh of stale words is in flight
-                for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    const unsigned bm = 0xffu << (PB * b);
-                    unsigned stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
-                    if (pending && (stale & bm)) {  // this batch needs the refreshed words: collect them now
-                        cp_async_wait_all();
-                        if (mine_pending) word = lds64(nq_mine);
-                        pending = mine_pending = false;
-                        stale = __ballot_sync(kFull, lane < nr && (unsigned)(word >> 32) != epoch);
-                    }
-                    // still not published: nothing else to do, poll with plain loads
-                    if ((stale & bm) && (lane >> 3) == b && lane < nr && (unsigned)(word >> 32) != epoch)
-                        word = poll_slow(wrow, epoch, p.status);
-                    const float val = __uint_as_float((unsigned)word);
-                    // re-request the stale words of the later batches asynchronously: the round trip overlaps
-                    // the pushes below
-                    const unsigned later = stale & ~(0xffffffffu << (PB * b));
-                    if (!pending && later) {
-                        mine_pending = (later >> lane) & 1u;
-                        if (mine_pending) cp_async16_s(nq_s, wrow16, 16);
-                        cp_async_commit();
-                        pending = true;
-                    }
-#pragma unroll
-                    for (int i = PB - 1; i >= 0; --i) {
-                        const int r = b * PB + i;
-                        const float vb = __shfl_sync(kFull, val, r);
-                        lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);
-                    }
-                }
-                cp_async_wait_all();  // drain before the FIFO is reused
-                lse_push(M, S, __shfl_sync(kFull, __uint_as_float((unsigned)word), 0) + eta_top, 1.0f);
-            }
+            if (has_next && c == BX - 1) lse_push(M, S, qnext + eta2, 1.0f);  // skip out of the top column
 #ifdef TKB_TIMELINE
             if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
                 p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 6] = globaltimer_ns();
@@ -585,7 +511,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #endif
             TKB_WSTAMP(5);
         }
-        __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
+        __syncthreads();  // partials (in the FIFOs), diagS and qtop are reused by the next owned block
     }
 }
 
