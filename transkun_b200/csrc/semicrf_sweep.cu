@@ -193,35 +193,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
         const int x0 = J * BX;
         const int ncols = min(BX, T - x0);
-        const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of the near tile (block J+1)
-        TKB_STAMP(0);
-
-        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
-        //         last block) are filled with -inf = "no candidate"
-        for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
-            const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
-            if (r > cc) {
-                if (r < ncols && (n0 + n) < N)
-                    cp_async4(&diagS[(n * BX + r) * BX + cc],
-                              p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
-                else
-                    diagS[(n * BX + r) * BX + cc] = -INFINITY;
-            }
-        }
-        cp_async_commit();
-        // unary + skip weights of my solver column (kept in registers across the far field)
-        const int c = lane;
+        const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of block J+1
+        const int c = lane;       // solver mapping: my column
         const int x = x0 + c;
-        // (parked in shared memory while the far field needs every register: a compiler spill would be
-        // re-read from L2 on the critical path, L1 being almost entirely carved out as shared memory)
-        {
-            const bool has_d = x < T && s_nok, has_e = has_d && x < T - 1;
-            cp_async4(&park[threadIdx.x], has_d ? p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn : p.Sbase,
-                      has_d ? 4 : 0);
-            cp_async4(&park[NT + threadIdx.x], has_e ? p.etabase + (long long)x * p.se + n0 + sn : p.Sbase,
-                      has_e ? 4 : 0);
-        }
-        cp_async_commit();
+        TKB_STAMP(0);
 
         // ---- A. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th pair ------------
         float vmax[2][4], lM[2][4], lS[2][4];
@@ -238,7 +213,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int R = T - (x0 + BX);              // rows y = T-1 .. x0+BX, taken in adjacent pairs
         const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
         const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
-        if (mypairs > 0) {
+        {
             // running source pointers of the next pair to issue (all 32 columns are valid here); pairs past
             // the end are issued with src-size 0 (no global access), so the loop body has no branches
             const float *sp0 = p.Sbase;
@@ -291,6 +266,34 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 issue();
                 cp_async_commit();
             }
+        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
+            //         last block) are filled with -inf = "no candidate"
+            for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
+                const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
+                if (r > cc) {
+                    if (r < ncols && (n0 + n) < N)
+                        cp_async4(&diagS[(n * BX + r) * BX + cc],
+                                  p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
+                    else
+                        diagS[(n * BX + r) * BX + cc] = -INFINITY;
+                }
+            }
+            cp_async_commit();
+            // unary + skip weights of my solver column
+            // (parked in shared memory while the far field needs every register: a compiler spill would be
+            // re-read from L2 on the critical path, L1 being almost entirely carved out as shared memory)
+            {
+                const bool has_d = x < T && s_nok, has_e = has_d && x < T - 1;
+                cp_async4(&park[threadIdx.x], has_d ? p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn : p.Sbase,
+                          has_d ? 4 : 0);
+                cp_async4(&park[NT + threadIdx.x], has_e ? p.etabase + (long long)x * p.se + n0 + sn : p.Sbase,
+                          has_e ? 4 : 0);
+            }
+            cp_async_commit();
+            // make the diagonal block and the parked constants visible to every warp now, so that each warp can
+            // do its solver set-up right after ITS far field instead of after the slowest warp's
+            cp_async_wait_all();
+            __syncthreads();
             int yA = T - 1 - 2 * warp;
             // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
             // and (log-sum) stage x = S*log2e + q for the chunk flush
@@ -372,16 +375,39 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 if (DO_V) my_partV[o] = make_float2(vmax[j][q], __int_as_float(vsel[j][q]));
                 if (DO_L) my_partL[o] = make_float2(lM[j][q], lS[j][q]);
             }
+        // ---- solver set-up that does not depend on the other warps: done BEFORE the barrier ---------------
+        // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows or
+        // columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
+        const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
+        const bool active = x < T;
+        const bool has_next = nr > 0;  // a later block exists: the top column can skip into row x0+BX
+        const float s_d = park[threadIdx.x], s_eta = park[NT + threadIdx.x];
+        float sreg[BX];  // my column of the diagonal block (log2 domain for the log-sum warps)
+        float u0, u1;    // Viterbi: relu(d), unused | log-sum: softplus(d)*log2e, eta*log2e
+        if (!s_is_lse) {
+#pragma unroll
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
+            u0 = relu_mask(s_d);
+            u1 = 0.0f;
+        } else {
+#pragma unroll
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
+            u0 = softplus_ref(s_d) * kLog2e;
+            u1 = s_eta * kLog2e;
+            // fold the skip into the coefficient of the row right above my column:
+            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
+            float sp = -INFINITY;
+#pragma unroll
+            for (int r = 1; r < BX; ++r) sp = (c == r - 1) ? sreg[r] : sp;
+            const float mx = fmaxf(sp, u1);
+            const float comb = (sp == -INFINITY) ? sp : mx + lg2f(1.0f + ex2f(-fabsf(sp - u1)));
+#pragma unroll
+            for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
+        }
         TKB_STAMP(1);
         TKB_WSTAMP(1);
         __syncthreads();
 
-        const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
-        const bool active = x < T;
-        const float s_d = park[threadIdx.x], s_eta = park[NT + threadIdx.x];
-        // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows
-        // or columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
-        const bool has_next = nr > 0;  // a later block exists: the top column can skip into row x0+BX
         const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
@@ -399,14 +425,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                     bsel = sl;
                 }
             }
-            float sreg[BX];
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
-            const float dr = relu_mask(s_d);
+            const float dr = u0;
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
             if (x == T - 1) best = -0.0f;
-            TKB_STAMP(2);
-            TKB_WSTAMP(3);
             // the skip out of the top column: candidate 0 of the reference, so it wins every tie
             if (has_next && c == BX - 1) {
                 const float xk = qnext + s_eta;
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 best = fmaxf(best, xk);
             }
             TKB_STAMP(3);
-            TKB_WSTAMP(4);
+            TKB_WSTAMP_DEP(4, best);
             // ---- D. diagonal solve: value chain = FADD -> SHFL -> FADD -> FMNMX ------------------
             float qmine = 0.0f;
 #pragma unroll
@@ -457,37 +478,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
             }
-            const float sp2 = softplus_ref(s_d) * kLog2e;
-            const float eta2 = s_eta * kLog2e;
-            float sreg[BX];
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
-            // fold the skip into the coefficient of the row right above my column:
-            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
-            {
-                float sp = -INFINITY;
-#pragma unroll
-                for (int r = 1; r < BX; ++r) sp = (c == r - 1) ? sreg[r] : sp;
-                const float mx = fmaxf(sp, eta2);
-                const float comb = (sp == -INFINITY) ? sp : mx + lg2f(1.0f + ex2f(-fabsf(sp - eta2)));
-#pragma unroll
-                for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
-            }
+            const float sp2 = u0, eta2 = u1;
             if (x == T - 1) {  // terminal column: value = softplus(S[T-1,T-1])
                 M = 0.0f;
                 S = 1.0f;
             }
-#ifdef TKB_TIMELINE
-            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
-                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 5] = globaltimer_ns();
-#endif
-            TKB_WSTAMP(3);
             if (has_next && c == BX - 1) lse_push(M, S, qnext + eta2, 1.0f);  // skip out of the top column
-#ifdef TKB_TIMELINE
-            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
-                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 6] = globaltimer_ns();
-#endif
-            TKB_WSTAMP(4);
+            TKB_WSTAMP_DEP(4, S);
             // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
 #pragma unroll
             for (int e = BX - 1; e >= 1; --e) {
@@ -505,10 +502,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
                 if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
             }
-#ifdef TKB_TIMELINE
-            if (threadIdx.x == 256 && p.timeline && owned_idx < 64)
-                p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + 7] = globaltimer_ns();
-#endif
             TKB_WSTAMP(5);
         }
         __syncthreads();  // partials (in the FIFOs), diagS and qtop are reused by the next owned block
