@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         } else {
 #pragma unroll
             for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
-            u0 = softplus_ref(s_d) * kLog2e;
+            {  // softplus(d)*log2e = max(d2,0) + log2(1 + 2^-|d2|), d2 = d*log2e
+                const float d2 = s_d * kLog2e;
+                u0 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));
+            }
             u1 = s_eta * kLog2e;
             // fold the skip into the coefficient of the row right above my column:
             // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
@@ -411,19 +414,31 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
-            float best = -INFINITY;
-            int bsel = -1;  // mirrored y of the best interval so far, -1 = none / skip
+            // branch-free 16-way merge: the maximum, then among the partials that attain it the row the
+            // reference's candidate order prefers (BACKWARD: smallest y, FORWARD: largest y).  Empty partials
+            // are (-inf, -1); (unsigned)-1 is the largest unsigned, so they never win the min.
+            float pv[NW];
+            int ps[NW];
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const float2 e = reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[sn * BX + c];
-                const int sl = __float_as_int(e.y);
-                const bool better = e.x > best ||
-                                    (e.x == best && sl >= 0 &&
-                                     ((DIR == TKB_BACKWARD) ? (bsel < 0 || sl < bsel) : (sl > bsel)));
-                if (better) {
-                    best = e.x;
-                    bsel = sl;
-                }
+                pv[w] = e.x;
+                ps[w] = __float_as_int(e.y);
+            }
+            float best = pv[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) best = fmaxf(best, pv[w]);
+            int bsel;  // mirrored y of the best interval so far, -1 = none / skip
+            if (DIR == TKB_BACKWARD) {
+                unsigned m = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) m = min(m, pv[w] == best ? (unsigned)ps[w] : 0xffffffffu);
+                bsel = (int)m;
+            } else {
+                int m = -1;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) m = max(m, pv[w] == best ? ps[w] : -1);
+                bsel = m;
             }
             const float dr = u0;
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
