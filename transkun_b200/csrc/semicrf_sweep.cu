@@ -55,7 +55,7 @@ constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][trac
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
-    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + kTileFloats * 4 +
+    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
     2 * NT * 4 + 2 * NG * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
     float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
-    float *park = diagS + kTileFloats;                                              // [2][NT] per-thread constants
+    float *diagL = diagS + kTileFloats;  // same block for the log-sum warps: *log2e, skip folded into row c+1
+    float *park = diagL + kTileFloats;                                              // [2][NT] per-thread constants
     float *qtop = park + 2 * NT;                                                    // [2][NG] q of row x0+BX
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,6 +295,23 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             // do its solver set-up right after ITS far field instead of after the slowest warp's
             cp_async_wait_all();
             __syncthreads();
+            if (DO_L) {
+                // log-sum copy of the diagonal block, prepared cooperatively and off the critical path:
+                // S*log2e, and the skip folded into the coefficient of the row right above each column:
+                // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
+                for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
+                    const int cc = i & 31, r = (i >> 5) & 31, n = i >> 10;
+                    if (r > cc) {
+                        float v = diagS[i] * kLog2e;
+                        if (r == cc + 1 && v != -INFINITY) {
+                            const float e2 = park[NT + (NG + n) * 32 + cc] * kLog2e;  // eta of column cc, track n
+                            v = fmaxf(v, e2) + lg2f(1.0f + ex2f(-fabsf(v - e2)));
+                        }
+                        diagL[i] = v;
+                    }
+                }
+                __syncthreads();  // diagL is read by the log-sum warps right after their own far field
+            }
             int yA = T - 1 - 2 * warp;
             // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
             // and (log-sum) stage x = S*log2e + q for the chunk flush
@@ -391,21 +409,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             u1 = 0.0f;
         } else {
 #pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagL[(sn * BX + r) * BX + c] : -INFINITY;
             {  // softplus(d)*log2e = max(d2,0) + log2(1 + 2^-|d2|), d2 = d*log2e
                 const float d2 = s_d * kLog2e;
                 u0 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));
             }
             u1 = s_eta * kLog2e;
-            // fold the skip into the coefficient of the row right above my column:
-            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
-            float sp = -INFINITY;
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sp = (c == r - 1) ? sreg[r] : sp;
-            const float mx = fmaxf(sp, u1);
-            const float comb = (sp == -INFINITY) ? sp : mx + lg2f(1.0f + ex2f(-fabsf(sp - u1)));
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
         }
         TKB_STAMP(1);
         TKB_WSTAMP(1);
