@@ -90,6 +90,7 @@ def time_cpu(T, N, steps, warmup, budget_s=60.0):
     from oracle import semicrf_oracle
     semicrf_oracle.build()
     score, noise = make_inputs("randn", T, N, 1234)
+    semicrf_oracle.lib().tko_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     cores = semicrf_oracle.lib().tko_max_threads()
     times = []
     t_begin = time.perf_counter()
@@ -179,9 +180,9 @@ def run_ours(args):
     import torch.distributed as dist
     from golden_util import make_inputs
     from transkun_b200 import _lib
-    from transkun_b200.CRF.NeuralSemiCRFInterval import NeuralSemiCRFInterval, backtrack, sweep
+    from transkun_b200.CRF.NeuralSemiCRFInterval import NeuralSemiCRFInterval, backtrack_records, sweep
     from transkun_b200._lib import BACKWARD, SWEEP_LOGSUM, SWEEP_VITERBI
-    from transkun_b200.sharded import gather_decoded, gather_vector, track_shard
+    from transkun_b200.sharded import gather_records, track_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,13 +217,10 @@ def run_ours(args):
         if record:
             e1.record(stream)
             ev_sweep.append((e0, e1))
-        pairs, counts = backtrack(code, None, BACKWARD)
-        logz = lse[0]
-        if world > 1:  # the only exchange: packed intervals + logZ, NCCL all-gather over NVLink
-            pairs, counts = gather_decoded(pairs, counts, n_total if args.scaling == "strong" else n_local * world,
-                                           max_pairs=None)
-            logz = gather_vector(logz, n_total if args.scaling == "strong" else n_local * world)
-        return pairs, counts, logz
+        rec = backtrack_records(code, None, BACKWARD, lse[0])  # [count, logZ, pairs] per track
+        if world > 1:  # the only exchange: one NCCL all-gather of the packed records over NVLink
+            rec = gather_records(rec, n_total)
+        return rec
 
     def fence():
         if world > 1:

@@ -102,6 +102,16 @@ int tkb_semicrf_backtrack(const uint32_t *code, int T, int N, const int32_t *for
                           int direction, int32_t *out_pairs, int32_t *out_counts, void *stream);
 
 /*
+ * Same, writing into caller-strided records: track n's pairs start at out_pairs + n*pair_stride
+ * (int32 units, pair_stride >= 4*T) and its count goes to out_counts[n*count_stride].  Lets a
+ * caller keep count, log-partition and pairs of a track in ONE fixed-size record, so that the
+ * multi-GPU gather of decoded intervals is a single zero-copy all-gather.
+ */
+int tkb_semicrf_backtrack_strided(const uint32_t *code, int T, int N, const int32_t *forced_start,
+                                  int direction, int32_t *out_pairs, int64_t pair_stride,
+                                  int32_t *out_counts, int64_t count_stride, void *stream);
+
+/*
  * Marginals (the custom gradient of the log-partition).  Replaces
  *   CRF/NeuralSemiCRFInterval.py:417-447 (forward_backward) fused with
  *   CRF/NeuralSemiCRFInterval.py:469-472 (ComputeLogZFasterGrad.backward).

@@ -38,6 +38,14 @@
 
 int tko_version(void) { return 1; }
 
+void tko_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int tko_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

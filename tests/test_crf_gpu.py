@@ -173,3 +173,21 @@ def test_fit_demo_converges():
     with torch.no_grad():
         assert NeuralSemiCRFInterval(score, noise).decode() == intervals
     assert abs(float(loss) - 1.59999) < 0.05  # the reference reaches 1.59999 after the same 400 steps (CPU)
+
+
+def test_packed_records_match_plain_backtrack():
+    """The strided ABI entry (one [count, logZ, pairs] record per track) gives the same pairs/counts."""
+    from transkun_b200.CRF.NeuralSemiCRFInterval import backtrack, backtrack_records, sweep
+    from transkun_b200._lib import BACKWARD, FORWARD, SWEEP_LOGSUM, SWEEP_VITERBI
+    from transkun_b200.sharded import split_records
+    score, noise = make_inputs("randn", 130, 20, 9)
+    s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
+    for direction in (BACKWARD, FORWARD):
+        code, _, lse, _ = sweep(s, z, direction, SWEEP_VITERBI | SWEEP_LOGSUM)
+        pairs, counts = backtrack(code, None, direction)
+        logz = lse[0 if direction == BACKWARD else 129]
+        rec = backtrack_records(code, None, direction, logz)
+        c2, z2, p2 = split_records(rec)
+        assert torch.equal(c2, counts) and torch.equal(z2, logz)
+        for n in range(20):
+            assert torch.equal(p2[n, : counts[n]], pairs[n, : counts[n]])

@@ -40,7 +40,7 @@ def _worker(rank, world, port, T, N, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle.semicrf_oracle import SemiCRFOracle
-        from transkun_b200.sharded import gather_decoded, gather_vector, track_shard
+        from transkun_b200.sharded import gather_decoded, gather_records, gather_vector, split_records, track_shard
         score, noise = make_inputs("randn", T, N, 21)
         lo, hi = track_shard(N, world, rank)
         o = SemiCRFOracle(score[:, :, lo:hi], noise[:, lo:hi])
@@ -55,6 +55,15 @@ def _worker(rank, world, port, T, N, q):
         ok &= bool(np.allclose(gz.numpy(), full.computeLogZ(), rtol=1e-6))
         gp2, _ = gather_decoded(torch.from_numpy(pairs), torch.from_numpy(counts), N, max_pairs=int(fc.max()))
         ok &= gp2.shape == (N, int(fc.max()), 2)
+        # single-collective record exchange: [count, logZ bits, pairs...] per track
+        rec = torch.zeros((hi - lo, 2 + 4 * T), dtype=torch.int32)
+        rec[:, 0] = torch.from_numpy(counts)
+        rec[:, 1] = torch.from_numpy(o.computeLogZ()).view(torch.int32)
+        rec[:, 2:] = torch.from_numpy(pairs).reshape(hi - lo, 4 * T)
+        rc, rz, rp = split_records(gather_records(rec, N))
+        ok &= bool(np.array_equal(rc.numpy(), fc)) and bool(np.allclose(rz.numpy(), full.computeLogZ(), rtol=1e-6))
+        for n in range(N):
+            ok &= bool(np.array_equal(rp[n, : fc[n]].numpy(), fp[n, : fc[n]]))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

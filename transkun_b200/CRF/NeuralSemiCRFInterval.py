@@ -115,6 +115,23 @@ def backtrack(code: torch.Tensor, forced: Optional[torch.Tensor], direction: int
     return pairs, counts
 
 
+def backtrack_records(code: torch.Tensor, forced: Optional[torch.Tensor], direction: int,
+                      logz: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Back-tracking into ONE fixed-size int32 record per track: [count, logZ bits, 4*T pair slots].
+    This is the unit the multi-GPU gather exchanges (transkun_b200.sharded.gather_records)."""
+    N, T = code.shape
+    dev = code.device
+    rec = torch.empty((N, 2 + 4 * T), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().tkb_semicrf_backtrack_strided(_ptr(code), T, N, _ptr(forced), direction,
+                                                       rec.data_ptr() + 8, 2 + 4 * T, rec.data_ptr(), 2 + 4 * T,
+                                                       _stream(dev))
+    _lib.check(rc, "tkb_semicrf_backtrack_strided")
+    if logz is not None:
+        rec[:, 1] = logz.contiguous().view(torch.int32)
+    return rec
+
+
 def _forced_tensor(forcedStartPos: Optional[Sequence[int]], N: int, T: int, dev) -> Optional[torch.Tensor]:
     if forcedStartPos is None:
         return None

@@ -19,7 +19,7 @@ SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
 # every symbol include/transkun_b200.h declares
 EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
-    "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
+    "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
     "tkb_semicrf_evalpath_grad",
 )
 
@@ -54,6 +54,8 @@ def load() -> ctypes.CDLL:
     L.tkb_sweep_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int), vp]
     L.tkb_semicrf_backtrack.restype = i
     L.tkb_semicrf_backtrack.argtypes = [vp, i, i, vp, i, vp, vp, vp]
+    L.tkb_semicrf_backtrack_strided.restype = i
+    L.tkb_semicrf_backtrack_strided.argtypes = [vp, i, i, vp, i, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]
     L.tkb_semicrf_marginals.restype = i
     L.tkb_semicrf_marginals.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     L.tkb_semicrf_evalpath.restype = i

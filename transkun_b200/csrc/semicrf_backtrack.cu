@@ -32,7 +32,8 @@ __device__ __forceinline__ T warp_scan_incl(T v, int lane) {
 
 __global__ void __launch_bounds__(BT_THREADS) backtrack_kernel(const unsigned *__restrict__ code, int T, int N,
                                                                const int *__restrict__ forced, int dir,
-                                                               int *__restrict__ pairs, int *__restrict__ counts) {
+                                                               int *__restrict__ pairs, int *__restrict__ counts,
+                                                               long long pair_stride, long long count_stride) {
     extern __shared__ int sm[];
     int *nxtA = sm;              // [T]
     int *nxtB = sm + T;          // [T]
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(BT_THREADS) backtrack_kernel(const unsigned *_
         total += t;
     }
     int k = woff + incl - local;
-    int *out = pairs + (size_t)n * 2 * T * 2;
+    int *out = pairs + (size_t)n * pair_stride;
     for (int u = ubeg; u < uend; ++u)
         if (mark[u]) {
             const unsigned w = cw[u];
@@ -114,16 +115,17 @@ __global__ void __launch_bounds__(BT_THREADS) backtrack_kernel(const unsigned *_
                 ++k;
             }
         }
-    if (tid == 0) counts[n] = total;
+    if (tid == 0) counts[(size_t)n * count_stride] = total;
 }
 
 }  // namespace tkb
 
 using namespace tkb;
 
-extern "C" int tkb_semicrf_backtrack(const uint32_t *code, int T, int N, const int32_t *forced_start, int direction,
-                                     int32_t *out_pairs, int32_t *out_counts, void *stream_) {
-    if (!code || !out_pairs || !out_counts || T < 1 || N < 1 ||
+static int launch_backtrack(const uint32_t *code, int T, int N, const int32_t *forced_start, int direction,
+                            int32_t *out_pairs, int32_t *out_counts, long long pair_stride, long long count_stride,
+                            void *stream_) {
+    if (!code || !out_pairs || !out_counts || T < 1 || N < 1 || pair_stride < 4ll * T || count_stride < 1 ||
         (direction != TKB_BACKWARD && direction != TKB_FORWARD)) {
         set_error("tkb_semicrf_backtrack: invalid argument (T=%d N=%d dir=%d)", T, N, direction);
         return TKB_EINVAL;
@@ -139,7 +141,19 @@ extern "C" int tkb_semicrf_backtrack(const uint32_t *code, int T, int N, const i
         configured = smem;
     }
     backtrack_kernel<<<N, BT_THREADS, smem, (cudaStream_t)stream_>>>(code, T, N, forced_start, direction, out_pairs,
-                                                                     out_counts);
+                                                                     out_counts, pair_stride, count_stride);
     TKB_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int tkb_semicrf_backtrack(const uint32_t *code, int T, int N, const int32_t *forced_start, int direction,
+                                     int32_t *out_pairs, int32_t *out_counts, void *stream_) {
+    return launch_backtrack(code, T, N, forced_start, direction, out_pairs, out_counts, 4ll * T, 1, stream_);
+}
+
+extern "C" int tkb_semicrf_backtrack_strided(const uint32_t *code, int T, int N, const int32_t *forced_start,
+                                             int direction, int32_t *out_pairs, int64_t pair_stride,
+                                             int32_t *out_counts, int64_t count_stride, void *stream_) {
+    return launch_backtrack(code, T, N, forced_start, direction, out_pairs, out_counts, pair_stride, count_stride,
+                            stream_);
 }

@@ -65,3 +65,27 @@ def gather_vector(v: torch.Tensor, n_tracks: int, group=None) -> torch.Tensor:
     dist.all_gather_into_tensor(out, buf, group=group)
     out = out.view(world, nmax)
     return torch.cat([out[r, :sizes[r]] for r in range(world)], 0)
+
+
+def gather_records(rec: torch.Tensor, n_tracks: int, group=None) -> torch.Tensor:
+    """All-gather fixed-size per-track records ([n_local, R] -> [n_tracks, R]) with ONE collective and no
+    packing copy when every rank owns the same number of tracks (the usual case: 88/8 = 11)."""
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_tracks, world)
+    nmax = max(sizes)
+    if rec.shape[0] != nmax:  # uneven shard: pad this rank's block
+        pad = torch.zeros((nmax, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+        pad[: rec.shape[0]] = rec
+        rec = pad
+    out = torch.empty((world * nmax, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    if min(sizes) == nmax:
+        return out
+    out = out.view(world, nmax, rec.shape[1])
+    return torch.cat([out[r, : sizes[r]] for r in range(world)], 0)
+
+
+def split_records(rec: torch.Tensor):
+    """(counts [N] int32, logZ [N] fp32, pairs [N, 2T, 2] int32) views of gathered records."""
+    T4 = rec.shape[1] - 2
+    return rec[:, 0], rec[:, 1].view(torch.float32), rec[:, 2:].view(rec.shape[0], T4 // 2, 2)
