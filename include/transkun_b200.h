@@ -140,6 +140,18 @@ int tkb_semicrf_evalpath_grad(int T, int N, const int32_t *pairs, const int64_t 
                               const float *gscale, float sign, float *grad_score, float *grad_noise,
                               void *stream);
 
+/*
+ * Scaled-Inner-Product interval scorer (tcgen05 / TMEM, TF32 operands, fp32 accumulate).  Replaces
+ * LayersTransformer.py:410-440 (everything of ScaledInnerProductIntervalScorer.forward after the
+ * Linear projection :406): per track n
+ *     out[e][b][n] = (sum_d q[n][e][d] * k[n][b][d]) / sqrt(D) * |e-b|  +  [e==b] * diag[n][e]
+ * q, k: [n_tracks][T][D] fp32 contiguous, 16-byte aligned, D a multiple of 32; diag: [n_tracks][T].
+ * out_score: [T][T][n_tracks] (the CRF's layout).  ONLY e >= b is written -- the only part the
+ * semi-CRF reads (the reference fills the full square).
+ */
+int tkb_sip_score(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
+                  float *out_score, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,110 @@
+"""Scaled-Inner-Product interval scorer: oracle vs the reference's golden outputs (CPU) and the tcgen05
+kernel vs the oracle (GPU, through the C ABI).  Tolerance: the kernel multiplies TF32 operands (10-bit
+mantissa, the reference's --allow_tf32 regime) and accumulates in fp32: |err| <= 2e-3 * max|S| per case;
+inputs that TF32 represents exactly (small integers) must come out bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sip_oracle import sip_forward
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "scorer_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_matches_reference(path):
+    z = np.load(path)
+    S, b = sip_forward(z["ctx"], z["weight"], z["bias"])
+    np.testing.assert_allclose(S, z["S"], rtol=1e-4, atol=1e-4)
+    assert b.shape == z["b"].shape and not z["b"].any()
+
+
+def _lower(S):
+    T = S.shape[0]
+    iu = np.tril_indices(T)
+    return S[iu[0], iu[1]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=lambda p: os.path.basename(p)[:-4])
+def test_kernel_matches_reference_module(path):
+    from transkun_b200.LayersTransformer import ScaledInnerProductIntervalScorer
+    z = np.load(path)
+    size = z["ctx"].shape[-1]
+    m = ScaledInnerProductIntervalScorer(size, 1).cuda()
+    m.load_state_dict({"map.0.weight": torch.from_numpy(z["weight"]), "map.0.bias": torch.from_numpy(z["bias"])})
+    with torch.no_grad():
+        S, b = m(torch.from_numpy(z["ctx"]).cuda())
+    assert S.shape == z["S"].shape and b.shape == z["b"].shape and not b.any()
+    got, want = _lower(S.cpu().numpy()), _lower(z["S"])
+    assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NT,T,D", [(8, 64, 32), (8, 128, 256), (3, 70, 64), (16, 200, 256), (90, 257, 256), (9, 129, 96)])
+def test_kernel_exact_on_tf32_representable_inputs(NT, T, D):
+    """Small-integer q/k are exact in TF32 and their dot products exact in fp32: every lower-triangle entry
+    must equal the fp32 reference formula bit for bit (isolates tiling / swizzle / descriptor / mask logic)."""
+    from transkun_b200.LayersTransformer import sip_score
+    g = torch.Generator().manual_seed(NT * 1000 + T)
+    q = torch.randint(-3, 4, (NT, T, D), generator=g).float()
+    k = torch.randint(-3, 4, (NT, T, D), generator=g).float()
+    diag = torch.randn(NT, T, generator=g)
+    S = sip_score(q.cuda(), k.cuda(), diag.cuda()).cpu()
+    t = torch.arange(T, dtype=torch.float32)
+    want = (torch.einsum("ned,nbd->neb", q, k) / (D ** 0.5)) * (t[:, None] - t[None, :]).abs()
+    want = (want + torch.diag_embed(diag)).permute(1, 2, 0)
+    tri = torch.tril(torch.ones(T, T, dtype=torch.bool))
+    if (D & (D - 1)) == 0 and int(D ** 0.5) ** 2 == D:   # 1/sqrt(D) exact
+        assert torch.equal(S[tri], want[tri])
+    else:
+        torch.testing.assert_close(S[tri], want[tri], rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_kernel_random_inputs_and_crf_roundtrip():
+    """Random fp32 inputs at the model's shape (T=691, 90 symbols, D=256): TF32 tolerance, and the scorer's
+    output feeds the CRF directly (same layout, lower triangle is all it reads)."""
+    from transkun_b200.CRF import NeuralSemiCRFInterval
+    from transkun_b200.LayersTransformer import ScaledInnerProductIntervalScorer
+    torch.manual_seed(0)
+    m = ScaledInnerProductIntervalScorer(256, 1).cuda()
+    ctx = torch.randn(1, 90, 691, 256, device="cuda") * 0.5
+    with torch.no_grad():
+        S, b = m(ctx)
+        W, bias = m.map[0].weight.double(), m.map[0].bias.double()
+        y = ctx.double() @ W.T + bias
+        qd, kd, dd = y[..., :256] / 16.0, y[..., 256:512], y[..., 512]
+        for p in (0, 45, 89):
+            ref = (qd[0, p] @ kd[0, p].T)
+            t = torch.arange(691, device="cuda", dtype=torch.float64)
+            ref = ref * (t[:, None] - t[None, :]).abs() + torch.diag(dd[0, p])
+            tri = torch.tril(torch.ones(691, 691, dtype=torch.bool, device="cuda"))
+            err = (S[:, :, 0, p].double() - ref)[tri].abs().max()
+            assert err <= 2e-3 * ref[tri].abs().max()
+        crf = NeuralSemiCRFInterval(S.flatten(-2, -1), b.flatten(-2, -1))
+        dec = crf.decode()
+        assert len(dec) == 90 and torch.isfinite(crf.computeLogZ(noBackward=True)).all()
+
+
+@pytest.mark.gpu
+def test_scorer_backward_matches_torch_formula():
+    from transkun_b200.LayersTransformer import ScaledInnerProductIntervalScorer
+    torch.manual_seed(1)
+    m = ScaledInnerProductIntervalScorer(64, 1).cuda()
+    ctx = torch.randn(1, 4, 50, 64, device="cuda", requires_grad=True)
+    S, _ = m(ctx)
+    w = torch.randn_like(S).tril_() if False else torch.randn_like(S)
+    tri = torch.tril(torch.ones(50, 50, device="cuda"))[:, :, None, None]
+    (S * w * tri).sum().backward()
+    g1 = ctx.grad.clone()
+    ctx.grad = None
+    y = m.map(ctx)
+    q, k, d = y[..., :64] / 8.0, y[..., 64:128], y[..., 128]
+    t = torch.arange(50, device="cuda", dtype=torch.float32)
+    S2 = torch.einsum("iped,ipbd->ipeb", q, k) * (t[:, None] - t[None, :]).abs() + torch.diag_embed(d)
+    (S2.permute(2, 3, 0, 1) * w * tri).sum().backward()
+    torch.testing.assert_close(g1, ctx.grad, rtol=2e-3, atol=2e-3)

@@ -1,0 +1,85 @@
+"""Scaled-Inner-Product interval scorer, B200-native.
+
+Drop-in for `transkun.LayersTransformer.ScaledInnerProductIntervalScorer`
+(/root/reference/transkun/LayersTransformer.py:381-441): same constructor, same parameter names
+(`map.0.weight [2*size*ef+1, size]`, `map.0.bias`), so the shipped checkpoint's `scorer.*` entries
+load unchanged, same forward signature `forward(ctx[B,P,T,D]) -> (S[T,T,B,P], b[T-1,B,P])`.
+
+The Linear projection (:406) is a plain library GEMM (torch/cuBLAS); everything after it -- the
+scaled q.k^T contraction, the |e-b| length factor, the diagonal and the permute into the CRF's
+[end, begin, batch, symbol] layout (:410-440) -- is ONE tcgen05/TMEM kernel (`tkb_sip_score`) that
+writes the lower triangle only (e >= b: all the semi-CRF reads; the reference fills the full square).
+TF32 operands, fp32 accumulation (the reference's own --allow_tf32 regime).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle defined)."""
+    if not (q.is_cuda and k.is_cuda and diag.is_cuda):
+        raise RuntimeError("transkun_b200 has no CPU path: scorer inputs must be CUDA tensors")
+    NT, T, D = q.shape
+    assert k.shape == (NT, T, D) and diag.shape == (NT, T)
+    q, k, diag = q.float().contiguous(), k.float().contiguous(), diag.float().contiguous()
+    if out is None:
+        out = torch.empty((T, T, NT), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.load().tkb_sip_score(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, D, out.data_ptr(),
+                                       torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(rc, "tkb_sip_score")
+    return out
+
+
+class _SipScoreFn(torch.autograd.Function):
+    """Forward: the tcgen05 kernel.  Backward (training path, not yet a custom kernel): the adjoint batched
+    GEMMs through torch on the lower triangle of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, q, k, diag):
+        ctx.save_for_backward(q, k)
+        return sip_score(q.detach(), k.detach(), diag.detach())
+
+    @staticmethod
+    def backward(ctx, gS):
+        q, k = ctx.saved_tensors
+        NT, T, D = q.shape
+        g = gS.permute(2, 0, 1).tril()  # [NT, e, b]; the forward only defines e >= b
+        t = torch.arange(T, device=q.device, dtype=torch.float32)
+        gl = g * (t[:, None] - t[None, :]).abs() / math.sqrt(D)
+        gq = torch.bmm(gl, k.float())
+        gk = torch.bmm(gl.transpose(1, 2), q.float())
+        gd = torch.diagonal(g, dim1=1, dim2=2)
+        return gq.to(q.dtype), gk.to(k.dtype), gd.contiguous()
+
+
+class ScaledInnerProductIntervalScorer(nn.Module):
+    def __init__(self, size, expansionFactor=1, dropoutProb=0.0, withScoreEps=False, lengthScaling="linear"):
+        super().__init__()
+        if withScoreEps or lengthScaling != "linear":
+            raise NotImplementedError("only the shipped configuration (withScoreEps=False, lengthScaling='linear')")
+        self.size = size
+        self.map = nn.Sequential(nn.Linear(size, 2 * size * expansionFactor + 1))  # q, k, diagonal (:390-392)
+        self.dropout = nn.Dropout(dropoutProb)  # never applied by the reference either
+        self.expansionFactor = expansionFactor
+        self.lengthScaling = lengthScaling
+
+    def forward(self, ctx):
+        # ctx: [B, P, T, size]
+        B, P, T, _ = ctx.shape
+        W, bias = self.map[0].weight, self.map[0].bias
+        d = self.size * self.expansionFactor
+        # three library GEMMs instead of one 513-wide one, so that q and k come out contiguous and 16-byte aligned
+        q = F.linear(ctx, W[:d], bias[:d]).reshape(B * P, T, d)
+        k = F.linear(ctx, W[d:2 * d], bias[d:2 * d]).reshape(B * P, T, d)
+        diag = F.linear(ctx, W[2 * d:], bias[2 * d:]).reshape(B * P, T)
+        S = _SipScoreFn.apply(q, k, diag).view(T, T, B, P)
+        b = torch.zeros((T - 1, B, P), dtype=S.dtype, device=S.device)  # "dummy eps score" (:434-436)
+        return S, b

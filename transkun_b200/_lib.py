@@ -20,7 +20,7 @@ SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
 EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
     "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
-    "tkb_semicrf_evalpath_grad",
+    "tkb_semicrf_evalpath_grad", "tkb_sip_score",
 )
 
 
@@ -62,6 +62,8 @@ def load() -> ctypes.CDLL:
     L.tkb_semicrf_evalpath.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp]
     L.tkb_semicrf_evalpath_grad.restype = i
     L.tkb_semicrf_evalpath_grad.argtypes = [i, i, vp, vp, vp, f, vp, vp, vp]
+    L.tkb_sip_score.restype = i
+    L.tkb_sip_score.argtypes = [vp, vp, vp, i, i, i, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
