@@ -152,6 +152,25 @@ int tkb_semicrf_evalpath_grad(int T, int N, const int32_t *pairs, const int64_t 
 int tkb_sip_score(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
                   float *out_score, void *stream);
 
+/*
+ * STFT / log-mel frontend.  Replaces Util.py:104-113 (Spectrum.forward) and :156-167
+ * (MelSpectrum.forward with log=True): for every frame, audio channel and window
+ *     X = rfft(frame * window, norm="ortho");  P = |X|^2;  (to_mono: mean over channels)
+ *     mel[m] = sum_f P[f] * melfb[f][m];  out = (log(mel+eps) - log(eps)) / (-log(eps))
+ * frames: element (b,c,f,i) at frames[b*stride_b + c*stride_c + f*stride_f + i] (float units; the
+ *   overlapping `unfold` view of makeFrame, Util.py:21-43, is read in place);
+ * windows [nWin][W]; melfb [W/2+1][nMel] dense row-major; band_lo/band_cnt [nMel]: first row and
+ *   number of rows of each mel filter's support (rows outside it are not read);
+ * out [B][to_mono ? 1 : C][F][nMel][nWin] fp32.
+ * workspace: tkb_logmel_workspace_bytes(B, C, F, W, nWin) bytes (windowed frames, spectra, cuFFT
+ *   work area).  The cuFFT plan for (W, B*C*F*nWin) is created on first use and cached.
+ */
+size_t tkb_logmel_workspace_bytes(int B, int C, int F, int W, int nWin);
+int tkb_logmel(const float *frames, int64_t stride_b, int64_t stride_c, int64_t stride_f, int B, int C,
+               int F, int W, const float *windows, int nWin, const float *melfb, const int32_t *band_lo,
+               const int32_t *band_cnt, int nMel, int to_mono, float eps, float *out, void *workspace,
+               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

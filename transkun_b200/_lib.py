@@ -20,7 +20,7 @@ SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
 EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
     "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
-    "tkb_semicrf_evalpath_grad", "tkb_sip_score",
+    "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_logmel_workspace_bytes", "tkb_logmel",
 )
 
 
@@ -41,6 +41,14 @@ def load() -> ctypes.CDLL:
             f"{_LIB_PATH} is missing: build it with `python -m transkun_b200.build` "
             "(nvcc, sm_100a). transkun_b200 has no CPU or PyTorch fallback.")
     import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library needs it)
+    # libcufft.so.11 (frontend): make sure it is resolvable whatever LD_LIBRARY_PATH says
+    for cand in ("libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11",
+                 os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cufft", "lib", "libcufft.so.11")):
+        try:
+            ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+            break
+        except OSError:
+            continue
     L = ctypes.CDLL(_LIB_PATH)
     vp, i, u32, sz, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_float
     L.tkb_version.restype = i
@@ -64,6 +72,11 @@ def load() -> ctypes.CDLL:
     L.tkb_semicrf_evalpath_grad.argtypes = [i, i, vp, vp, vp, f, vp, vp, vp]
     L.tkb_sip_score.restype = i
     L.tkb_sip_score.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    i64 = ctypes.c_int64
+    L.tkb_logmel_workspace_bytes.restype = sz
+    L.tkb_logmel_workspace_bytes.argtypes = [i, i, i, i, i]
+    L.tkb_logmel.restype = i
+    L.tkb_logmel.argtypes = [vp, i64, i64, i64, i, i, i, i, vp, i, vp, vp, vp, i, i, f, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

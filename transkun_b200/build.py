@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if not force and out == LIB and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-o", out, *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-o", out, *sources(), "-lcufft"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
