@@ -46,7 +46,7 @@ constexpr int CH = 2;      // rows per log-sum-exp rescale chunk (= one row pair
 constexpr int PB = 8;      // rows per publish batch
 
 // shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
-// diagonal block transposed to [track][row][col] | parked per-thread constants | q of the row above the block.
+// diagonal block and near tile (rows of block J+1), transposed to [track][row][col] | parked per-thread constants.
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
@@ -56,7 +56,7 @@ constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
     kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
-    2 * NT * 4 + 2 * NG * 4;
+    2 * NT * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -160,9 +160,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
     float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
-    float *diagL = diagS + kTileFloats;  // same block for the log-sum warps: *log2e, skip folded into row c+1
-    float *park = diagL + kTileFloats;                                              // [2][NT] per-thread constants
-    float *qtop = park + 2 * NT;                                                    // [2][NG] q of row x0+BX
+    float *nearS = diagS + kTileFloats;  // rows of block J+1 x my columns, same layout
+    float *park = nearS + kTileFloats;                                              // [2][NT] per-thread constants
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int x = x0 + c;
         TKB_STAMP(0);
 
-        // ---- A. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th pair ------------
+        // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th pair ----------
         float vmax[2][4], lM[2][4], lS[2][4];
         int vsel[2][4];
 #pragma unroll
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lM[j][q] = -FLT_MAX;
                 lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + BX);              // rows y = T-1 .. x0+BX, taken in adjacent pairs
+        const int R = T - (x0 + 2 * BX);          // rows y = T-1 .. x0+2*BX, taken in adjacent pairs
         const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
         const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
         {
@@ -267,17 +266,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 issue();
                 cp_async_commit();
             }
-        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
-            //         last block) are filled with -inf = "no candidate"
+        // ---- 0. prefetch the diagonal block and the near tile (rows of block J+1), transposed to
+            //         [track][row][col]; rows beyond T (only in the last two blocks) are -inf = "no candidate"
             for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
                 const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
+                const bool nok = (n0 + n) < N;
+                const float *src = p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
                 if (r > cc) {
-                    if (r < ncols && (n0 + n) < N)
-                        cp_async4(&diagS[(n * BX + r) * BX + cc],
-                                  p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
-                    else
-                        diagS[(n * BX + r) * BX + cc] = -INFINITY;
+                    if (r < ncols && nok) cp_async4(&diagS[(n * BX + r) * BX + cc], src, 4);
+                    else diagS[(n * BX + r) * BX + cc] = -INFINITY;
                 }
+                if (r < nr && nok) cp_async4(&nearS[(n * BX + r) * BX + cc], src + (long long)BX * p.sy, 4);
+                else nearS[(n * BX + r) * BX + cc] = -INFINITY;
             }
             cp_async_commit();
             // unary + skip weights of my solver column
@@ -295,23 +295,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             // do its solver set-up right after ITS far field instead of after the slowest warp's
             cp_async_wait_all();
             __syncthreads();
-            if (DO_L) {
-                // log-sum copy of the diagonal block, prepared cooperatively and off the critical path:
-                // S*log2e, and the skip folded into the coefficient of the row right above each column:
-                // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
-                for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
-                    const int cc = i & 31, r = (i >> 5) & 31, n = i >> 10;
-                    if (r > cc) {
-                        float v = diagS[i] * kLog2e;
-                        if (r == cc + 1 && v != -INFINITY) {
-                            const float e2 = park[NT + (NG + n) * 32 + cc] * kLog2e;  // eta of column cc, track n
-                            v = fmaxf(v, e2) + lg2f(1.0f + ex2f(-fabsf(v - e2)));
-                        }
-                        diagL[i] = v;
-                    }
-                }
-                __syncthreads();  // diagL is read by the log-sum warps right after their own far field
-            }
             int yA = T - 1 - 2 * warp;
             // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
             // and (log-sum) stage x = S*log2e + q for the chunk flush
@@ -328,13 +311,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
                     if (!ok) {
                         const unsigned long long *w = cq + (size_t)(yA - c_row) * p.Npad;
-                        word = (yA < x0 + 3 * BX) ? poll_slow<0>(w, epoch, p.status)
+                        word = (yA < x0 + 4 * BX) ? poll_slow<0>(w, epoch, p.status)
                                                   : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
                     }
                 }
                 const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
                 sts32(qc_s + so * 128 + lane * 4, qrow);
-                if (yA - c_row == x0 + BX) qtop[lane & 15] = qrow;  // [kind][track] of row x0+BX
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
@@ -409,18 +391,42 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             u1 = 0.0f;
         } else {
 #pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagL[(sn * BX + r) * BX + c] : -INFINITY;
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
             {  // softplus(d)*log2e = max(d2,0) + log2(1 + 2^-|d2|), d2 = d*log2e
                 const float d2 = s_d * kLog2e;
                 u0 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));
             }
             u1 = s_eta * kLog2e;
+            // fold the skip into the coefficient of the row right above my column:
+            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
+            const float sp = (c < BX - 1) ? diagS[(sn * BX + c + 1) * BX + c] * kLog2e : -INFINITY;
+            const float comb = (sp == -INFINITY) ? sp : fmaxf(sp, u1) + lg2f(1.0f + ex2f(-fabsf(sp - u1)));
+#pragma unroll
+            for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
         }
         TKB_STAMP(1);
         TKB_WSTAMP(1);
         __syncthreads();
 
-        const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
+        // ---- C. near tile: the 32 rows of block J+1, read by the solver warps straight from the mailbox.
+        // Lane i polls the word of row x0+BX+i (my track, my semiring); every pass refreshes ALL still-stale
+        // words, so that rows published meanwhile cost no extra round trip; only the batch about to be pushed
+        // is waited for.  Everything above (far field, barrier, merge) was finished a whole block-step ago.
+        const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
+        unsigned long long word = 0;
+        auto near_wait = [&](int b) {  // returns when rows 8b..8b+7 of the near tile are valid in `word`
+            const unsigned bm = 0xffu << (PB * b);
+            for (int it = 0;; ++it) {
+                const bool stale = lane < nr && (unsigned)(word >> 32) != epoch;
+                const unsigned st = __ballot_sync(kFull, stale);
+                if (!(st & bm)) break;
+                if (it < 256) {
+                    if (stale) word = ld_relaxed_u64(wrow);
+                } else {
+                    if (stale && ((bm >> lane) & 1u)) word = poll_slow<0>(wrow, epoch, p.status);  // watchdog path
+                }
+            }
+        };
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
             // branch-free 16-way merge: the maximum, then among the partials that attain it the row the
@@ -452,9 +458,24 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const float dr = u0;
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
             if (x == T - 1) best = -0.0f;
-            // the skip out of the top column: candidate 0 of the reference, so it wins every tie
-            if (has_next && c == BX - 1) {
-                const float xk = qnext + s_eta;
+            if (has_next) {
+                TKB_WSTAMP(3);
+                for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    near_wait(b);
+                    const float val = __uint_as_float((unsigned)word);
+#pragma unroll
+                    for (int i = PB - 1; i >= 0; --i) {
+                        const int r = b * PB + i;
+                        const float qb = __shfl_sync(kFull, val, r);
+                        const float xi = qb + nearS[(sn * BX + r) * BX + c];  // -inf for rows beyond T
+                        const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
+                        bsel = tk ? x0 + BX + r : bsel;
+                        best = fmaxf(best, xi);
+                    }
+                }
+                // the skip out of the top column: candidate 0 of the reference, so it wins every tie
+                const float q0 = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0);  // q of row x0+BX
+                const float xk = (c == BX - 1) ? q0 + s_eta : -INFINITY;
                 bsel = (xk >= best) ? -1 : bsel;
                 best = fmaxf(best, xk);
             }
@@ -507,7 +528,21 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 M = 0.0f;
                 S = 1.0f;
             }
-            if (has_next && c == BX - 1) lse_push(M, S, qnext + eta2, 1.0f);  // skip out of the top column
+            if (has_next) {
+                TKB_WSTAMP(3);
+                for (int b = (BX / PB) - 1; b >= 0; --b) {
+                    near_wait(b);
+                    const float val = __uint_as_float((unsigned)word);
+#pragma unroll
+                    for (int i = PB - 1; i >= 0; --i) {
+                        const int r = b * PB + i;
+                        const float vb = __shfl_sync(kFull, val, r);
+                        lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);  // -inf: no-op
+                    }
+                }
+                const float v0 = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0);
+                lse_push(M, S, (c == BX - 1) ? v0 + eta2 : -INFINITY, 1.0f);  // skip out of the top column
+            }
             TKB_WSTAMP_DEP(4, S);
             // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
 #pragma unroll
@@ -528,7 +563,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             }
             TKB_WSTAMP(5);
         }
-        __syncthreads();  // partials (in the FIFOs), diagS and qtop are reused by the next owned block
+        __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
     }
 }
 
