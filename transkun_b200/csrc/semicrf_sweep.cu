@@ -30,7 +30,8 @@
 //          the chain, the skip weight is folded into the coefficient of the row right
 //          above a column, and rows are published in batches of 8 (one lg2 per batch);
 //   * solved rows are broadcast to the other CTAs of the group through a
-//     global-memory mailbox of 64-bit words {fp32 value, epoch tag}: one relaxed
+//     global-memory mailbox (track-major: a solver warp's 32 rows are two cache lines, a
+//     published batch of 8 rows is one 64-byte store) of 64-bit words {fp32 value, epoch tag}: one relaxed
 //     store publishes, one relaxed load observes (no fence, no flag, no reset).
 // All CTAs of a launch must be co-resident (cooperative launch).
 #include "common.cuh"
@@ -51,7 +52,7 @@ constexpr int PB = 8;      // rows per publish batch
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
-constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][track] tagged words
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 64;  // [slot][32 lanes] 16-byte chunks of tagged words
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
@@ -66,9 +67,9 @@ struct SweepParams {
     const float *Sbase;    // &S(0,0) in mirrored coordinates
     const float *etabase;  // &skip weight of x = 0
     long long sx, sy, se;  // element strides
-    int T, N, Npad, G, K, g0, dir;
+    int T, Tpad, N, Npad, G, K, g0, dir;  // Tpad = T rounded up to even: 16-byte aligned track rows in the mailbox
     unsigned epoch;
-    unsigned long long *mbox;  // [2][T][Npad] {value, epoch}
+    unsigned long long *mbox;  // [2 semirings][Npad tracks][T] {value, epoch}: track-major, see below
     int *status;
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int n0 = g * NG;
     const unsigned epoch = p.epoch;
     unsigned long long *mboxV = p.mbox;
-    unsigned long long *mboxL = p.mbox + (size_t)T * p.Npad;
+    unsigned long long *mboxL = p.mbox + (size_t)p.Tpad * p.Npad;  // each track's words are contiguous
 
     // far-field mapping: lane -> (column pair, track quad)
     const int cpair = lane >> 1, quad = lane & 1;
@@ -185,9 +186,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
     const bool s_nok = (n0 + sn) < N;
-    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + n0 + sn;  // + row * Npad
+    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + (size_t)(n0 + sn) * p.Tpad;  // + row
     const long long row_step = (long long)NW * p.sy;
-    const long long q_step = (long long)NW * p.Npad;
 
     int owned_idx = 0;
     for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
@@ -222,18 +222,20 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const long long sstep = nvalid > 0 ? 2 * row_step : 0;
             const long long scol = nvalid > 0 ? p.sx : 0;
             const long long srow = nvalid > 0 ? p.sy : 0;
-            // mailbox fetch: lane = row*8 + kind*4 + track pair (lanes 0-15); tag check: lane = row*16 + kind*8 + track
-            const int f_row = lane >> 3, f_kind = (lane >> 2) & 1;
-            const bool qfetch = lane < 16 && (f_kind ? DO_L : DO_V);
-            const unsigned long long *qp =
-                (f_kind ? mboxL : mboxV) + (size_t)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
-            const int c_row = lane >> 4, c_kind = (lane >> 3) & 1;
+            // mailbox: lane = kind*16 + track*2 + row-of-the-pair.  The mailbox is track-major, so the lane fetches
+            // the aligned 16-byte chunk (two consecutive rows of its track) that contains its row and later
+            // checks / uses exactly that word.  Rows step by 2*NW = 32 per iteration: the parity never changes.
+            const int c_kind = lane >> 4, c_trk = (lane >> 1) & 7, c_row = lane & 1;
             const bool c_need = c_kind ? DO_L : DO_V;
-            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + n0 + (lane & 7);  // + y * Npad
+            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + (size_t)(n0 + c_trk) * p.Tpad;  // + y
+            const int c_y0 = T - 1 - 2 * warp - c_row;            // my row in the first pair (may be < 0: never live)
+            const unsigned c_off = (unsigned)(c_y0 & 1) * 8u;     // byte offset of my word inside the 16-byte chunk
+            const unsigned long long *qp = cq + (c_y0 & ~1);      // chunk of the next pair to issue
+            const unsigned c_dst = (unsigned)(c_row * 16 + c_kind * 8 + c_trk) * 4u;  // compact [row][kind][track]
             const float c_absent = c_kind ? -FLT_MAX : -INFINITY;  // q of a row that does not exist
             const int nbytes = nvalid * 4;
             const unsigned ring_s = smem_u32(my_ring);  // + slot*2048 + row*1024 + col*512
-            const unsigned q_s = smem_u32(my_q);        // + slot*256: tagged words [row][kind][track]
+            const unsigned q_s = smem_u32(my_q);        // + slot*512 + lane*16: my chunk
             const unsigned qc_s = smem_u32(my_qc);      // + slot*128: untagged values [row][kind][track]
             int ti = 0;  // next pair to issue
             auto issue = [&]() {
@@ -256,9 +258,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         cp_async4_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
                     }
                 }
-                if (qfetch) cp_async16_s(q_s + (so >> 3) + lane * 16, qp, (f_row ? liveB : live) ? 16 : 0);
+                if (c_need) cp_async16_s(q_s + (so >> 2) + lane * 16, qp, (c_row ? liveB : live) ? 16 : 0);
                 sp0 -= sstep;
-                qp -= 2 * q_step;
+                qp -= 2 * NW;
                 ++ti;
             };
 #pragma unroll
@@ -305,18 +307,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 __syncwarp();
                 const unsigned so = (unsigned)(t & (SLOTS - 1));
                 const bool hasB = 2 * (warp + t * NW) + 1 < R;
-                unsigned long long word = lds64(q_s + so * 256 + lane * 8);
+                unsigned long long word = lds64(q_s + so * 512 + lane * 16 + c_off);
                 const bool need = c_need && (c_row == 0 || hasB);
                 const bool ok = !need || (unsigned)(word >> 32) == epoch;
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
                     if (!ok) {
-                        const unsigned long long *w = cq + (size_t)(yA - c_row) * p.Npad;
+                        const unsigned long long *w = cq + (yA - c_row);
                         word = (yA < x0 + 4 * BX) ? poll_slow<0>(w, epoch, p.status)
                                                   : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
                     }
                 }
                 const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
-                sts32(qc_s + so * 128 + lane * 4, qrow);
+                sts32(qc_s + so * 128 + c_dst, qrow);
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         // Lane i polls the word of row x0+BX+i (my track, my semiring); every pass refreshes ALL still-stale
         // words, so that rows published meanwhile cost no extra round trip; only the batch about to be pushed
         // is waited for.  Everything above (far field, barrier, merge) was finished a whole block-step ago.
-        const unsigned long long *wrow = s_mbox + (size_t)(x0 + BX + lane) * p.Npad;
+        const unsigned long long *wrow = s_mbox + (x0 + BX + lane);  // 32 consecutive words: two cache lines
         unsigned long long word = 0;
         auto near_wait = [&](int b) {  // returns when rows 8b..8b+7 of the near tile are valid in `word`
             const unsigned bm = 0xffu << (PB * b);
@@ -496,10 +498,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 bsel = (xk >= b1) ? -1 : bsel;
                 best = fmaxf(b1, xk);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active)
-                    publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
+                    publish(s_mbox + x, qmine, epoch);
             }
             qmine = (c == 0) ? best + dr : qmine;
-            if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
+            if (c < PB && active) publish(s_mbox + x, qmine, epoch);
             TKB_STAMP(4);
             TKB_WSTAMP(5);
             if (active && s_nok) {
@@ -552,13 +554,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lse_push(M, S, Mb + sreg[e], sb);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active) {
                     const float v2 = (M + sp2) + lg2f(S);
-                    publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
+                    publish(s_mbox + x, v2, epoch);
                     if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
                 }
             }
             if (c < PB && active) {
                 const float v2 = (M + sp2) + lg2f(S);
-                publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
+                publish(s_mbox + x, v2, epoch);
                 if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
             }
             TKB_WSTAMP(5);
@@ -611,7 +613,7 @@ using namespace tkb;
 extern "C" size_t tkb_sweep_workspace_bytes(int T, int N) {
     if (T < 1 || N < 1) return 0;
     const size_t npad = (size_t)((N + NG - 1) / NG) * NG;
-    return kHeaderBytes + 2 * (size_t)T * npad * sizeof(unsigned long long);
+    return kHeaderBytes + 2 * (size_t)((T + 1) & ~1) * npad * sizeof(unsigned long long);
 }
 
 extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
@@ -636,6 +638,7 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
     p.N = N;
     p.G = (N + NG - 1) / NG;
     p.Npad = p.G * NG;
+    p.Tpad = (T + 1) & ~1;
     p.dir = direction;
     p.epoch = epoch;
     p.status = reinterpret_cast<int *>(workspace);
