@@ -60,7 +60,7 @@ print(f"L: prev L solve_done -> my far_done mean {np.mean(rows[1:,3]-rows[:-1,9]
       f"L setup done -> near done {np.mean(rows[:,8]-rows[:,7]):.2f}")
 
 # per-warp stamps for a few mid-run blocks of group 0:
-# far loop done | set-up done, at the barrier | merged, near tile starts | near tile done, solve starts | solve done
+# far loop done | set-up done, at the barrier | merged (solve starts) | solve done
 print("\nper-warp stamps relative to the PREVIOUS block's latest solve_done (us); warps 0-7 Viterbi, 8-15 log-sum")
 for J in (40, 39, 20, 8):
     if J + 1 > nb - 1:
@@ -73,4 +73,4 @@ for J in (40, 39, 20, 8):
     print(f"block J={J}: prev block solve_done V {0.0:.2f} L {(refL - refV) / 1e3:.2f} (rel. to prev V done); "
           f"block J+2 solve_done V {(wt[kpp, idxpp, :8, 5].max() - refV) / 1e3:.2f} L {(wt[kpp, idxpp, 8:, 5].max() - refV) / 1e3:.2f}")
     for w in range(16):
-        print(f"  warp {w:2d}: " + " ".join(f"{(wt[k, idx, w, sidx] - refV) / 1e3:8.2f}" for sidx in (0, 1, 3, 4, 5)))
+        print(f"  warp {w:2d}: " + " ".join(f"{(wt[k, idx, w, sidx] - refV) / 1e3:8.2f}" for sidx in (0, 1, 4, 5)))

@@ -30,8 +30,7 @@
 //          the chain, the skip weight is folded into the coefficient of the row right
 //          above a column, and rows are published in batches of 8 (one lg2 per batch);
 //   * solved rows are broadcast to the other CTAs of the group through a
-//     global-memory mailbox (track-major: a solver warp's 32 rows are two cache lines, a
-//     published batch of 8 rows is one 64-byte store) of 64-bit words {fp32 value, epoch tag}: one relaxed
+//     global-memory mailbox of 64-bit words {fp32 value, epoch tag}: one relaxed
 //     store publishes, one relaxed load observes (no fence, no flag, no reset).
 // All CTAs of a launch must be co-resident (cooperative launch).
 #include "common.cuh"
@@ -47,17 +46,17 @@ constexpr int CH = 2;      // rows per log-sum-exp rescale chunk (= one row pair
 constexpr int PB = 8;      // rows per publish batch
 
 // shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
-// diagonal block and near tile (rows of block J+1), transposed to [track][row][col] | parked per-thread constants.
+// diagonal block transposed to [track][row][col] | parked per-thread constants | q of the row above the block.
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
 // solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
-constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 64;  // [slot][32 lanes] 16-byte chunks of tagged words
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][track] tagged words
 constexpr size_t kTileFloats = (size_t)NG * BX * BX;
 constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
 constexpr size_t kSweepSmem =
     kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
-    2 * NT * 4;
+    2 * NT * 4 + 2 * NG * 4;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -67,9 +66,9 @@ struct SweepParams {
     const float *Sbase;    // &S(0,0) in mirrored coordinates
     const float *etabase;  // &skip weight of x = 0
     long long sx, sy, se;  // element strides
-    int T, Tpad, N, Npad, G, K, g0, dir;  // Tpad = T rounded up to even: 16-byte aligned track rows in the mailbox
+    int T, N, Npad, G, K, g0, dir;
     unsigned epoch;
-    unsigned long long *mbox;  // [2 semirings][Npad tracks][T] {value, epoch}: track-major, see below
+    unsigned long long *mbox;  // [2][T][Npad] {value, epoch}
     int *status;
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
@@ -161,8 +160,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
     float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
-    float *nearS = diagS + kTileFloats;  // rows of block J+1 x my columns, same layout
-    float *park = nearS + kTileFloats;                                              // [2][NT] per-thread constants
+    float *diagL = diagS + kTileFloats;  // same block for the log-sum warps: *log2e, skip folded into row c+1
+    float *park = diagL + kTileFloats;                                              // [2][NT] per-thread constants
+    float *qtop = park + 2 * NT;                                                    // [2][NG] q of row x0+BX
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int n0 = g * NG;
     const unsigned epoch = p.epoch;
     unsigned long long *mboxV = p.mbox;
-    unsigned long long *mboxL = p.mbox + (size_t)p.Tpad * p.Npad;  // each track's words are contiguous
+    unsigned long long *mboxL = p.mbox + (size_t)T * p.Npad;
 
     // far-field mapping: lane -> (column pair, track quad)
     const int cpair = lane >> 1, quad = lane & 1;
@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
     const bool s_nok = (n0 + sn) < N;
-    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + (size_t)(n0 + sn) * p.Tpad;  // + row
+    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + n0 + sn;  // + row * Npad
     const long long row_step = (long long)NW * p.sy;
+    const long long q_step = (long long)NW * p.Npad;
 
     int owned_idx = 0;
     for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
         const int x = x0 + c;
         TKB_STAMP(0);
 
-        // ---- A. far field: rows y = T-1 .. x0+2*BX, this warp takes every NW-th pair ----------
+        // ---- A. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th pair ------------
         float vmax[2][4], lM[2][4], lS[2][4];
         int vsel[2][4];
 #pragma unroll
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lM[j][q] = -FLT_MAX;
                 lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + 2 * BX);          // rows y = T-1 .. x0+2*BX, taken in adjacent pairs
+        const int R = T - (x0 + BX);              // rows y = T-1 .. x0+BX, taken in adjacent pairs
         const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
         const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
         {
@@ -222,20 +223,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const long long sstep = nvalid > 0 ? 2 * row_step : 0;
             const long long scol = nvalid > 0 ? p.sx : 0;
             const long long srow = nvalid > 0 ? p.sy : 0;
-            // mailbox: lane = kind*16 + track*2 + row-of-the-pair.  The mailbox is track-major, so the lane fetches
-            // the aligned 16-byte chunk (two consecutive rows of its track) that contains its row and later
-            // checks / uses exactly that word.  Rows step by 2*NW = 32 per iteration: the parity never changes.
-            const int c_kind = lane >> 4, c_trk = (lane >> 1) & 7, c_row = lane & 1;
+            // mailbox fetch: lane = row*8 + kind*4 + track pair (lanes 0-15); tag check: lane = row*16 + kind*8 + track
+            const int f_row = lane >> 3, f_kind = (lane >> 2) & 1;
+            const bool qfetch = lane < 16 && (f_kind ? DO_L : DO_V);
+            const unsigned long long *qp =
+                (f_kind ? mboxL : mboxV) + (size_t)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
+            const int c_row = lane >> 4, c_kind = (lane >> 3) & 1;
             const bool c_need = c_kind ? DO_L : DO_V;
-            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + (size_t)(n0 + c_trk) * p.Tpad;  // + y
-            const int c_y0 = T - 1 - 2 * warp - c_row;            // my row in the first pair (may be < 0: never live)
-            const unsigned c_off = (unsigned)(c_y0 & 1) * 8u;     // byte offset of my word inside the 16-byte chunk
-            const unsigned long long *qp = cq + (c_y0 & ~1);      // chunk of the next pair to issue
-            const unsigned c_dst = (unsigned)(c_row * 16 + c_kind * 8 + c_trk) * 4u;  // compact [row][kind][track]
+            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + n0 + (lane & 7);  // + y * Npad
             const float c_absent = c_kind ? -FLT_MAX : -INFINITY;  // q of a row that does not exist
             const int nbytes = nvalid * 4;
             const unsigned ring_s = smem_u32(my_ring);  // + slot*2048 + row*1024 + col*512
-            const unsigned q_s = smem_u32(my_q);        // + slot*512 + lane*16: my chunk
+            const unsigned q_s = smem_u32(my_q);        // + slot*256: tagged words [row][kind][track]
             const unsigned qc_s = smem_u32(my_qc);      // + slot*128: untagged values [row][kind][track]
             int ti = 0;  // next pair to issue
             auto issue = [&]() {
@@ -258,9 +257,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                         cp_async4_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
                     }
                 }
-                if (c_need) cp_async16_s(q_s + (so >> 2) + lane * 16, qp, (c_row ? liveB : live) ? 16 : 0);
+                if (qfetch) cp_async16_s(q_s + (so >> 3) + lane * 16, qp, (f_row ? liveB : live) ? 16 : 0);
                 sp0 -= sstep;
-                qp -= 2 * NW;
+                qp -= 2 * q_step;
                 ++ti;
             };
 #pragma unroll
@@ -268,18 +267,17 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 issue();
                 cp_async_commit();
             }
-        // ---- 0. prefetch the diagonal block and the near tile (rows of block J+1), transposed to
-            //         [track][row][col]; rows beyond T (only in the last two blocks) are -inf = "no candidate"
+        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
+            //         last block) are filled with -inf = "no candidate"
             for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
                 const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
-                const bool nok = (n0 + n) < N;
-                const float *src = p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n;
                 if (r > cc) {
-                    if (r < ncols && nok) cp_async4(&diagS[(n * BX + r) * BX + cc], src, 4);
-                    else diagS[(n * BX + r) * BX + cc] = -INFINITY;
+                    if (r < ncols && (n0 + n) < N)
+                        cp_async4(&diagS[(n * BX + r) * BX + cc],
+                                  p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
+                    else
+                        diagS[(n * BX + r) * BX + cc] = -INFINITY;
                 }
-                if (r < nr && nok) cp_async4(&nearS[(n * BX + r) * BX + cc], src + (long long)BX * p.sy, 4);
-                else nearS[(n * BX + r) * BX + cc] = -INFINITY;
             }
             cp_async_commit();
             // unary + skip weights of my solver column
@@ -297,6 +295,23 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             // do its solver set-up right after ITS far field instead of after the slowest warp's
             cp_async_wait_all();
             __syncthreads();
+            if (DO_L) {
+                // log-sum copy of the diagonal block, prepared cooperatively and off the critical path:
+                // S*log2e, and the skip folded into the coefficient of the row right above each column:
+                // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
+                for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
+                    const int cc = i & 31, r = (i >> 5) & 31, n = i >> 10;
+                    if (r > cc) {
+                        float v = diagS[i] * kLog2e;
+                        if (r == cc + 1 && v != -INFINITY) {
+                            const float e2 = park[NT + (NG + n) * 32 + cc] * kLog2e;  // eta of column cc, track n
+                            v = fmaxf(v, e2) + lg2f(1.0f + ex2f(-fabsf(v - e2)));
+                        }
+                        diagL[i] = v;
+                    }
+                }
+                __syncthreads();  // diagL is read by the log-sum warps right after their own far field
+            }
             int yA = T - 1 - 2 * warp;
             // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
             // and (log-sum) stage x = S*log2e + q for the chunk flush
@@ -307,18 +322,19 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 __syncwarp();
                 const unsigned so = (unsigned)(t & (SLOTS - 1));
                 const bool hasB = 2 * (warp + t * NW) + 1 < R;
-                unsigned long long word = lds64(q_s + so * 512 + lane * 16 + c_off);
+                unsigned long long word = lds64(q_s + so * 256 + lane * 8);
                 const bool need = c_need && (c_row == 0 || hasB);
                 const bool ok = !need || (unsigned)(word >> 32) == epoch;
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
                     if (!ok) {
-                        const unsigned long long *w = cq + (yA - c_row);
-                        word = (yA < x0 + 4 * BX) ? poll_slow<0>(w, epoch, p.status)
+                        const unsigned long long *w = cq + (size_t)(yA - c_row) * p.Npad;
+                        word = (yA < x0 + 3 * BX) ? poll_slow<0>(w, epoch, p.status)
                                                   : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
                     }
                 }
                 const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
-                sts32(qc_s + so * 128 + c_dst, qrow);
+                sts32(qc_s + so * 128 + lane * 4, qrow);
+                if (yA - c_row == x0 + BX) qtop[lane & 15] = qrow;  // [kind][track] of row x0+BX
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
@@ -393,42 +409,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             u1 = 0.0f;
         } else {
 #pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] * kLog2e : -INFINITY;
+            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagL[(sn * BX + r) * BX + c] : -INFINITY;
             {  // softplus(d)*log2e = max(d2,0) + log2(1 + 2^-|d2|), d2 = d*log2e
                 const float d2 = s_d * kLog2e;
                 u0 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));
             }
             u1 = s_eta * kLog2e;
-            // fold the skip into the coefficient of the row right above my column:
-            // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
-            const float sp = (c < BX - 1) ? diagS[(sn * BX + c + 1) * BX + c] * kLog2e : -INFINITY;
-            const float comb = (sp == -INFINITY) ? sp : fmaxf(sp, u1) + lg2f(1.0f + ex2f(-fabsf(sp - u1)));
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (c == r - 1) ? comb : sreg[r];
         }
         TKB_STAMP(1);
         TKB_WSTAMP(1);
         __syncthreads();
 
-        // ---- C. near tile: the 32 rows of block J+1, read by the solver warps straight from the mailbox.
-        // Lane i polls the word of row x0+BX+i (my track, my semiring); every pass refreshes ALL still-stale
-        // words, so that rows published meanwhile cost no extra round trip; only the batch about to be pushed
-        // is waited for.  Everything above (far field, barrier, merge) was finished a whole block-step ago.
-        const unsigned long long *wrow = s_mbox + (x0 + BX + lane);  // 32 consecutive words: two cache lines
-        unsigned long long word = 0;
-        auto near_wait = [&](int b) {  // returns when rows 8b..8b+7 of the near tile are valid in `word`
-            const unsigned bm = 0xffu << (PB * b);
-            for (int it = 0;; ++it) {
-                const bool stale = lane < nr && (unsigned)(word >> 32) != epoch;
-                const unsigned st = __ballot_sync(kFull, stale);
-                if (!(st & bm)) break;
-                if (it < 256) {
-                    if (stale) word = ld_relaxed_u64(wrow);
-                } else {
-                    if (stale && ((bm >> lane) & 1u)) word = poll_slow<0>(wrow, epoch, p.status);  // watchdog path
-                }
-            }
-        };
+        const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
         if (!s_is_lse && DO_V) {
             // ================= Viterbi: (max,+), bit-exact fp32 =================================
             // branch-free 16-way merge: the maximum, then among the partials that attain it the row the
@@ -460,24 +452,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const float dr = u0;
             // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
             if (x == T - 1) best = -0.0f;
-            if (has_next) {
-                TKB_WSTAMP(3);
-                for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    near_wait(b);
-                    const float val = __uint_as_float((unsigned)word);
-#pragma unroll
-                    for (int i = PB - 1; i >= 0; --i) {
-                        const int r = b * PB + i;
-                        const float qb = __shfl_sync(kFull, val, r);
-                        const float xi = qb + nearS[(sn * BX + r) * BX + c];  // -inf for rows beyond T
-                        const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
-                        bsel = tk ? x0 + BX + r : bsel;
-                        best = fmaxf(best, xi);
-                    }
-                }
-                // the skip out of the top column: candidate 0 of the reference, so it wins every tie
-                const float q0 = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0);  // q of row x0+BX
-                const float xk = (c == BX - 1) ? q0 + s_eta : -INFINITY;
+            // the skip out of the top column: candidate 0 of the reference, so it wins every tie
+            if (has_next && c == BX - 1) {
+                const float xk = qnext + s_eta;
                 bsel = (xk >= best) ? -1 : bsel;
                 best = fmaxf(best, xk);
             }
@@ -498,10 +475,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 bsel = (xk >= b1) ? -1 : bsel;
                 best = fmaxf(b1, xk);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active)
-                    publish(s_mbox + x, qmine, epoch);
+                    publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
             }
             qmine = (c == 0) ? best + dr : qmine;
-            if (c < PB && active) publish(s_mbox + x, qmine, epoch);
+            if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
             TKB_STAMP(4);
             TKB_WSTAMP(5);
             if (active && s_nok) {
@@ -530,21 +507,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 M = 0.0f;
                 S = 1.0f;
             }
-            if (has_next) {
-                TKB_WSTAMP(3);
-                for (int b = (BX / PB) - 1; b >= 0; --b) {
-                    near_wait(b);
-                    const float val = __uint_as_float((unsigned)word);
-#pragma unroll
-                    for (int i = PB - 1; i >= 0; --i) {
-                        const int r = b * PB + i;
-                        const float vb = __shfl_sync(kFull, val, r);
-                        lse_push(M, S, fmaf(nearS[(sn * BX + r) * BX + c], kLog2e, vb), 1.0f);  // -inf: no-op
-                    }
-                }
-                const float v0 = __shfl_sync(kFull, __uint_as_float((unsigned)word), 0);
-                lse_push(M, S, (c == BX - 1) ? v0 + eta2 : -INFINITY, 1.0f);  // skip out of the top column
-            }
+            if (has_next && c == BX - 1) lse_push(M, S, qnext + eta2, 1.0f);  // skip out of the top column
             TKB_WSTAMP_DEP(4, S);
             // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
 #pragma unroll
@@ -554,18 +517,18 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lse_push(M, S, Mb + sreg[e], sb);
                 if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active) {
                     const float v2 = (M + sp2) + lg2f(S);
-                    publish(s_mbox + x, v2, epoch);
+                    publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
                     if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
                 }
             }
             if (c < PB && active) {
                 const float v2 = (M + sp2) + lg2f(S);
-                publish(s_mbox + x, v2, epoch);
+                publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
                 if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
             }
             TKB_WSTAMP(5);
         }
-        __syncthreads();  // partials (in the FIFOs), diagS and nearS are reused by the next owned block
+        __syncthreads();  // partials (in the FIFOs), diagS and qtop are reused by the next owned block
     }
 }
 
@@ -613,7 +576,7 @@ using namespace tkb;
 extern "C" size_t tkb_sweep_workspace_bytes(int T, int N) {
     if (T < 1 || N < 1) return 0;
     const size_t npad = (size_t)((N + NG - 1) / NG) * NG;
-    return kHeaderBytes + 2 * (size_t)((T + 1) & ~1) * npad * sizeof(unsigned long long);
+    return kHeaderBytes + 2 * (size_t)T * npad * sizeof(unsigned long long);
 }
 
 extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
@@ -638,7 +601,6 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
     p.N = N;
     p.G = (N + NG - 1) / NG;
     p.Npad = p.G * NG;
-    p.Tpad = (T + 1) & ~1;
     p.dir = direction;
     p.epoch = epoch;
     p.status = reinterpret_cast<int *>(workspace);
