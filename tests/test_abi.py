@@ -33,9 +33,9 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_sizes(lib):
     assert lib.tkb_version() == 1
-    # header + 2 semirings * T * ceil8(N) * 8 bytes
-    assert lib.tkb_sweep_workspace_bytes(2048, 88) == 256 + 2 * 2048 * 88 * 8
-    assert lib.tkb_sweep_workspace_bytes(10, 9) == 256 + 2 * 10 * 16 * 8
+    # header + row mailbox (2 semirings * T * ceil8(N) words) + far partials (groups * blocks * 2 * 8 * 32 * 2 words)
+    assert lib.tkb_sweep_workspace_bytes(2048, 88) == 256 + 2 * 2048 * 88 * 8 + 11 * 64 * 2 * 8 * 32 * 2 * 8
+    assert lib.tkb_sweep_workspace_bytes(10, 9) == 256 + 2 * 10 * 16 * 8 + 2 * 1 * 2 * 8 * 32 * 2 * 8
     assert lib.tkb_sweep_workspace_bytes(0, 4) == 0
 
 

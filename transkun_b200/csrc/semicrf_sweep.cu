@@ -1,11 +1,11 @@
-// semicrf_sweep.cu -- the semi-Markov dynamic programme as ONE persistent kernel.
+// semicrf_sweep.cu -- the semi-Markov dynamic programme as ONE persistent kernel (solver / helper CTAs).
 //
 // Replaces the TorchScript step loops of the reference
 // (transkun/CRF/NeuralSemiCRFInterval.py:31-51, :124-144, :218-234, :303-327):
 //     q[x] = ( skip(x)  (+)  (+)_{y>x} q[y] (x) S(y,x) )  (x)  unary(x)
-// over the (max,+) semiring (Viterbi, bit-exact fp32: one add per candidate,
-// exact max, the reference's tie order) and the (logsumexp,+) semiring
-// (log-partition), both fed by a single read of the score triangle.
+// over the (max,+) semiring (Viterbi, bit-exact fp32: one add per candidate, exact max, the
+// reference's tie order) and the (logsumexp,+) semiring (log-partition), both fed by a single
+// read of the score triangle.
 //
 // Mirrored coordinates.  x is the position being solved, y > x a solved one.
 //   BACKWARD: x = begin b, y = end e, S(y,x) = score[e][b]      (sx = N,    sy = T*N)
@@ -13,74 +13,82 @@
 //                                                               (sx = -T*N, sy = -N)
 // so one kernel serves viterbiBackward/beta and viterbi/alpha.
 //
-// It is a lower-triangular solve, not a map: T strictly sequential steps.
-// Decomposition:
-//   * tracks are independent -> groups of NG=8 tracks (one 32-byte sector of the
-//     track-innermost layout) form independent pipelines;
-//   * per group, K CTAs own the 32-column blocks round-robin (block J -> CTA
-//     (nb-1-J) mod K).  For its block J a CTA runs three phases:
-//       A  FAR FIELD: all rows y in later blocks (order-free semiring mat-vec, the bulk
-//          of the bytes): 16 warps each own every 16th PAIR of adjacent rows,
-//          cp.async-staged into per-lane shared-memory FIFOs together with the
-//          mailbox rows, accumulators in registers;
-//       B  the 16 partials are merged into the solver mapping: one warp per
-//          (track, semiring), lane = column;
-//       D  DIAGONAL SOLVE: 31 dependent steps, one shuffle each, branch-free.  The
-//          log-sum chain carries (M, S) pairs (value = M + log2 S) so no log sits on
-//          the chain, the skip weight is folded into the coefficient of the row right
-//          above a column, and rows are published in batches of 8 (one lg2 per batch);
-//   * solved rows are broadcast to the other CTAs of the group through a
-//     global-memory mailbox of 64-bit words {fp32 value, epoch tag}: one relaxed
-//     store publishes, one relaxed load observes (no fence, no flag, no reset).
+// It is a lower-triangular solve: T strictly sequential steps per track.  The design keeps that
+// chain inside ONE SM from the first to the last position, and lets every other SM stream the
+// triangle:
+//   * tracks are independent; a GROUP is 8 tracks = one 32-byte sector of the track-innermost layout;
+//   * per group two SOLVER CTAs (4 tracks = 16 bytes each) run the chain: one warp per track, lane =
+//     column of the current 32-column block, V and L semirings interleaved in the same instruction
+//     stream.  A chain step broadcasts the just-finished row with shuffles and pushes it into the
+//     current block (the diagonal tile, on the chain) and into the next ND blocks (off the chain); the
+//     score values come from a shared-memory ring of "row bands" (32 rows x (ND+1)*32 columns x 16 B)
+//     that four loader warps of the same CTA keep filled with cp.async, mbarrier-synchronised;
+//   * per group H HELPER CTAs own the column blocks round-robin and stream everything further than ND
+//     blocks above the diagonal (the bulk of the bytes): 16 warps, each every 16th pair of rows,
+//     cp.async FIFOs, register accumulators, merged once per block and handed to the solvers as a
+//     "far partial";
+//   * rows travel solver -> helpers through a global-memory mailbox of 64-bit words {fp32 value, epoch},
+//     far partials travel helper -> solver the same way: one relaxed store publishes, one relaxed load
+//     observes (no fence, no flag, no reset; the epoch grows with every launch).
 // All CTAs of a launch must be co-resident (cooperative launch).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tkb {
 
 constexpr int NG = 8;      // tracks per group
-constexpr int BX = 32;     // columns per block (= lanes of a solver warp)
-constexpr int NW = 16;     // warps per CTA: far field 16 row-slices; solve 8 tracks x 2 semirings
+constexpr int NQ = 4;      // tracks per solver CTA
+constexpr int BX = 32;     // columns per block (= lanes of a chain warp)
+#ifndef TKB_ND
+#define TKB_ND 2
+#endif
+constexpr int ND = TKB_ND;  // blocks above the diagonal block that the solver pushes itself
+constexpr int NBAND = (ND == 2) ? 4 : 3;  // row bands resident in a solver CTA
+constexpr int BANDCOLS = (ND + 1) * BX;
+constexpr int NW = 16;     // warps per CTA (helper: 16 row slices; solver: 4 chain + 4 loader warps)
 constexpr int NT = NW * 32;
-constexpr int SLOTS = 4;   // per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
-constexpr int CH = 2;      // rows per log-sum-exp rescale chunk (= one row pair)
+constexpr int NCW = NQ;    // chain warps
+constexpr int NLW = 4;     // loader warps
+constexpr int SLOTS = 4;   // helper: per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
 constexpr int PB = 8;      // rows per publish batch
 
-// shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (128 B per row) |
-// diagonal block transposed to [track][row][col] | parked per-thread constants | q of the row above the block.
+// helper shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (tagged) | untagged copy.
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
-// solver: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
+// merge: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
 constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
 constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
-constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;  // [slot][row][kind][track] tagged words
-constexpr size_t kTileFloats = (size_t)NG * BX * BX;
-constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy: [slot][row][kind][track]
-constexpr size_t kSweepSmem =
-    kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4 + 2 * kTileFloats * 4 +
-    2 * NT * 4 + 2 * NG * 4;
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;    // [slot][row][kind][track] tagged words
+constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy, same layout
+constexpr size_t kHelperSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4;
+// solver shared memory: row bands [NBAND][BX rows][BANDCOLS][NQ tracks] | mbarriers full[NBAND], empty[NBAND]
+constexpr size_t kBandBytes = (size_t)BX * BANDCOLS * NQ * 4;
+constexpr size_t kSolverSmem = (size_t)NBAND * kBandBytes + 2 * NBAND * 8;
+constexpr size_t kSweepSmem = kHelperSmem > kSolverSmem ? kHelperSmem : kSolverSmem;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
+static_assert(kSweepSmem <= 227 * 1024, "shared memory budget");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
-#define TKB_TIMELINE_STAMPS 8
 
 struct SweepParams {
     const float *Sbase;    // &S(0,0) in mirrored coordinates
     const float *etabase;  // &skip weight of x = 0
     long long sx, sy, se;  // element strides
-    int T, N, Npad, G, K, g0, dir;
+    int T, N, Npad, G, H, g0, dir;
     unsigned epoch;
-    unsigned long long *mbox;  // [2][T][Npad] {value, epoch}
+    unsigned long long *mbox;  // [2 semirings][T][Npad] {value, epoch}
+    unsigned long long *part;  // [G][nb][2 semirings][NG][BX][2] {value, epoch}: far partials
     int *status;
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
     float *outl;     // [T][N] or null
-    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][8] globaltimer stamps
+    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][4] globaltimer stamps
 };
 
-// Wait until the mailbox word carries this launch's epoch.  A protocol bug (or a
-// non-co-resident grid) must not hang the GPU: after ~4 s the wait gives up,
-// flags the workspace and lets the kernel drain with garbage.
-// BACKOFF_NS > 0 is for waits that are NOT on the critical path (far-field rows): hundreds of warps spinning
-// on the few mailbox lines the chain is currently writing slow the chain's own reader and writer down.
+// Wait until a mailbox word carries this launch's epoch.  A protocol bug (or a non-co-resident grid) must not
+// hang the GPU: after ~4 s the wait gives up, flags the workspace and lets the kernel drain with garbage.
+// BACKOFF_NS > 0 is for waits that are NOT close to a deadline (far rows): hundreds of warps spinning on the few
+// mailbox lines the chain is currently writing slow the chain's own writer down.
 template <int BACKOFF_NS>
 __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w, unsigned epoch, int *status) {
     unsigned long long t0 = globaltimer_ns();
@@ -104,35 +112,64 @@ __device__ __forceinline__ void publish(unsigned long long *w, float val, unsign
     st_relaxed_u64(w, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val));
 }
 
+// ---- mbarrier (shared::cta) -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrival that fires once all cp.async issued so far by this thread have landed (count pre-charged at init)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// same watchdog as poll_slow: a protocol bug must drain the kernel, not hang the GPU
+__device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity, int *status) {
+    unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        for (int i = 0; i < 1024; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (*(volatile int *)status != 0) return;
+        if (globaltimer_ns() - t0 > 4000000000ull) {
+            atomicExch(status, 2);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int *status) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, status);
+}
+__device__ __forceinline__ void cp_async8_s(unsigned saddr, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
 #ifdef TKB_TIMELINE
-#define TKB_STAMP(slot)                                                                                     \
-    do {                                                                                                    \
-        if (threadIdx.x == 0 && p.timeline && owned_idx < 64)                                               \
-            p.timeline[((size_t)blockIdx.x * 64 + owned_idx) * TKB_TIMELINE_STAMPS + (slot)] = globaltimer_ns(); \
-    } while (0)
-// per-warp stamps: timeline + 148*64*8 words, laid out [grid][64][NW][8]
-#define TKB_WSTAMP(slot)                                                                                        \
-    do {                                                                                                        \
-        if (lane == 0 && p.timeline && owned_idx < 64)                                                          \
-            p.timeline[(size_t)148 * 64 * 8 + (((size_t)blockIdx.x * 64 + owned_idx) * NW + warp) * 8 + (slot)] = \
-                globaltimer_ns();                                                                               \
-    } while (0)
-// stamp that cannot be taken before `dep` (a register value) is available
-#define TKB_WSTAMP_DEP(slot, dep)                                                                               \
-    do {                                                                                                        \
-        if (lane == 0 && p.timeline && owned_idx < 64)                                                          \
-            p.timeline[(size_t)148 * 64 * 8 + (((size_t)blockIdx.x * 64 + owned_idx) * NW + warp) * 8 + (slot)] = \
-                globaltimer_ns() + ((__float_as_uint(dep) == 0x7fedcba9u) ? 1ull : 0ull);                       \
+// [grid][64 owned blocks / 64 chain blocks][4] stamps
+#define TKB_STAMP(idx, slot)                                                                    \
+    do {                                                                                        \
+        if (p.timeline && (idx) < 64) p.timeline[((size_t)blockIdx.x * 64 + (idx)) * 4 + (slot)] = globaltimer_ns(); \
     } while (0)
 #else
-#define TKB_WSTAMP_DEP(slot, dep) \
-    do {                          \
-    } while (0)
-#define TKB_STAMP(slot) \
-    do {                \
-    } while (0)
-#define TKB_WSTAMP(slot) \
-    do {                 \
+#define TKB_STAMP(idx, slot) \
+    do {                     \
     } while (0)
 #endif
 
@@ -144,29 +181,22 @@ __device__ __forceinline__ void lse_push(float &M, float &S, float a, float sb) 
     M = fmaxf(M, a);
 }
 
-template <int DIR, bool A16, int MODE>
-__global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
+// =================================================================================================
+// HELPER: far partial of the owned column blocks
+// =================================================================================================
+template <int DIR, int ALIGN, int MODE>
+__device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char *smem_raw, int g, int h) {
     constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
     constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
-#ifdef TKB_PREFETCH_D
-    constexpr int D = TKB_PREFETCH_D;  // tuning builds
-#else
+    constexpr bool A16 = ALIGN == 16;
     constexpr int D = SLOTS - 1;
-#endif
-    static_assert(D >= 1 && D <= SLOTS - 1, "prefetch distance must leave one FIFO slot free");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     float *ring = reinterpret_cast<float *>(smem_raw);
     unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
     float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
-    float *diagS = qcomp + (size_t)NW * kQcFloatsPerWarp;  // [NG][BX rows][BX cols]
-    float *diagL = diagS + kTileFloats;  // same block for the log-sum warps: *log2e, skip folded into row c+1
-    float *park = diagL + kTileFloats;                                              // [2][NT] per-thread constants
-    float *qtop = park + 2 * NT;                                                    // [2][NG] q of row x0+BX
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
-    const int g = p.g0 + (int)blockIdx.x / p.K, k = (int)blockIdx.x % p.K;
     const int nb = (T + BX - 1) / BX;
     const int n0 = g * NG;
     const unsigned epoch = p.epoch;
@@ -178,28 +208,20 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     const int nq = n0 + quad * 4;
     const int nvalid = min(max(N - nq, 0), 4);
     float *my_ring = ring + (size_t)warp * kRingFloatsPerWarp + lane * 4;  // + slot*256 (+128 for column 1)
-    unsigned long long *my_q = qring + (size_t)warp * kQWordsPerWarp;      // + slot*16 + {0..7 V, 8..15 L}
+    unsigned long long *my_q = qring + (size_t)warp * kQWordsPerWarp;
     float *my_qc = qcomp + (size_t)warp * kQcFloatsPerWarp;
     float2 *my_partV = reinterpret_cast<float2 *>(ring + (size_t)warp * kRingFloatsPerWarp);  // [NG][BX]
     float2 *my_partL = my_partV + NG * BX;
-    // solver mapping: warp -> (semiring, track), lane -> column
+    // merge mapping: warp -> (semiring, track), lane -> column
     const int sn = warp & 7;
     const bool s_is_lse = warp >= 8;
-    const bool s_nok = (n0 + sn) < N;
-    unsigned long long *s_mbox = (s_is_lse ? mboxL : mboxV) + n0 + sn;  // + row * Npad
     const long long row_step = (long long)NW * p.sy;
     const long long q_step = (long long)NW * p.Npad;
 
     int owned_idx = 0;
-    for (int J = nb - 1 - k; J >= 0; J -= p.K, ++owned_idx) {
+    for (int J = nb - ND - 2 - h; J >= 0; J -= p.H, ++owned_idx) {
         const int x0 = J * BX;
-        const int ncols = min(BX, T - x0);
-        const int nr = min(BX, max(T - (x0 + BX), 0));  // rows of block J+1
-        const int c = lane;       // solver mapping: my column
-        const int x = x0 + c;
-        TKB_STAMP(0);
-
-        // ---- A. far field: rows y = T-1 .. x0+BX, this warp takes every NW-th pair ------------
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 0);
         float vmax[2][4], lM[2][4], lS[2][4];
         int vsel[2][4];
 #pragma unroll
@@ -211,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 lM[j][q] = -FLT_MAX;
                 lS[j][q] = 0.0f;
             }
-        const int R = T - (x0 + BX);              // rows y = T-1 .. x0+BX, taken in adjacent pairs
+        const int R = T - (x0 + (ND + 1) * BX);   // rows y = T-1 .. x0+(ND+1)*BX, taken in adjacent pairs (R >= 1)
         const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
         const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
         {
@@ -227,9 +249,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             const int f_row = lane >> 3, f_kind = (lane >> 2) & 1;
             const bool qfetch = lane < 16 && (f_kind ? DO_L : DO_V);
             const unsigned long long *qp =
-                (f_kind ? mboxL : mboxV) + (size_t)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
+                (f_kind ? mboxL : mboxV) + (long long)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
             const int c_row = lane >> 4, c_kind = (lane >> 3) & 1;
-            const bool c_need = c_kind ? DO_L : DO_V;
+            const bool c_need = (c_kind ? DO_L : DO_V) && (n0 + (lane & 7)) < N;  // padding tracks are never published
             const unsigned long long *cq = (c_kind ? mboxL : mboxV) + n0 + (lane & 7);  // + y * Npad
             const float c_absent = c_kind ? -FLT_MAX : -INFINITY;  // q of a row that does not exist
             const int nbytes = nvalid * 4;
@@ -246,6 +268,16 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                     cp_async16_s(ring_s + so + 512, sp0 + scol, live ? nbytes : 0);
                     cp_async16_s(ring_s + so + 1024, sp0 - srow, liveB ? nbytes : 0);
                     cp_async16_s(ring_s + so + 1536, sp0 - srow + scol, liveB ? nbytes : 0);
+                } else if (ALIGN == 8) {
+#pragma unroll
+                    for (int q = 0; q < 4; q += 2) {
+                        const int qq = q < nvalid ? q : 0;
+                        const int nA = (live && q < nvalid) ? 8 : 0, nB = (liveB && q < nvalid) ? 8 : 0;
+                        cp_async8_s(ring_s + so + q * 4, sp0 + qq, nA);
+                        cp_async8_s(ring_s + so + 512 + q * 4, sp0 + scol + qq, nA);
+                        cp_async8_s(ring_s + so + 1024 + q * 4, sp0 - srow + qq, nB);
+                        cp_async8_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -267,54 +299,9 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 issue();
                 cp_async_commit();
             }
-        // ---- 0. prefetch the diagonal block, transposed to [track][row][col]; rows beyond T (only in the
-            //         last block) are filled with -inf = "no candidate"
-            for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
-                const int n = i & 7, cc = (i >> 3) & 31, r = i >> 8;
-                if (r > cc) {
-                    if (r < ncols && (n0 + n) < N)
-                        cp_async4(&diagS[(n * BX + r) * BX + cc],
-                                  p.Sbase + (long long)(x0 + cc) * p.sx + (long long)(x0 + r) * p.sy + n0 + n, 4);
-                    else
-                        diagS[(n * BX + r) * BX + cc] = -INFINITY;
-                }
-            }
-            cp_async_commit();
-            // unary + skip weights of my solver column
-            // (parked in shared memory while the far field needs every register: a compiler spill would be
-            // re-read from L2 on the critical path, L1 being almost entirely carved out as shared memory)
-            {
-                const bool has_d = x < T && s_nok, has_e = has_d && x < T - 1;
-                cp_async4(&park[threadIdx.x], has_d ? p.Sbase + (long long)x * (p.sx + p.sy) + n0 + sn : p.Sbase,
-                          has_d ? 4 : 0);
-                cp_async4(&park[NT + threadIdx.x], has_e ? p.etabase + (long long)x * p.se + n0 + sn : p.Sbase,
-                          has_e ? 4 : 0);
-            }
-            cp_async_commit();
-            // make the diagonal block and the parked constants visible to every warp now, so that each warp can
-            // do its solver set-up right after ITS far field instead of after the slowest warp's
-            cp_async_wait_all();
-            __syncthreads();
-            if (DO_L) {
-                // log-sum copy of the diagonal block, prepared cooperatively and off the critical path:
-                // S*log2e, and the skip folded into the coefficient of the row right above each column:
-                // v[y] + S2(y,x)  (+)  v[y] + eta2(x)  =  v[y] + log2(2^S2 + 2^eta2)
-                for (int i = threadIdx.x; i < BX * BX * NG; i += NT) {
-                    const int cc = i & 31, r = (i >> 5) & 31, n = i >> 10;
-                    if (r > cc) {
-                        float v = diagS[i] * kLog2e;
-                        if (r == cc + 1 && v != -INFINITY) {
-                            const float e2 = park[NT + (NG + n) * 32 + cc] * kLog2e;  // eta of column cc, track n
-                            v = fmaxf(v, e2) + lg2f(1.0f + ex2f(-fabsf(v - e2)));
-                        }
-                        diagL[i] = v;
-                    }
-                }
-                __syncthreads();  // diagL is read by the log-sum warps right after their own far field
-            }
             int yA = T - 1 - 2 * warp;
             // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
-            // and (log-sum) stage x = S*log2e + q for the chunk flush
+            // and (log-sum) stage x = S*log2e + q for the pair flush
             auto do_pair = [&](int t, float (&xlA)[2][4], float (&xlB)[2][4]) {
                 issue();
                 cp_async_commit();
@@ -327,14 +314,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 const bool ok = !need || (unsigned)(word >> 32) == epoch;
                 if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
                     if (!ok) {
-                        const unsigned long long *w = cq + (size_t)(yA - c_row) * p.Npad;
-                        word = (yA < x0 + 3 * BX) ? poll_slow<0>(w, epoch, p.status)
-                                                  : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
+                        const unsigned long long *w = cq + (long long)(yA - c_row) * p.Npad;
+                        word = (yA < x0 + (ND + 3) * BX) ? poll_slow<0>(w, epoch, p.status)
+                                                         : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
                     }
                 }
                 const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
                 sts32(qc_s + so * 128 + lane * 4, qrow);
-                if (yA - c_row == x0 + BX) qtop[lane & 15] = qrow;  // [kind][track] of row x0+BX
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
@@ -363,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 yA -= 2 * NW;
             };
             for (int t = 0; t < mypairs; ++t) {  // one max/rescale per pair of rows
-                float xl[CH][2][4];
+                float xl[2][2][4];
                 do_pair(t, xl[0], xl[1]);
                 if (DO_L) {
 #pragma unroll
@@ -381,8 +367,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 }
             }
         }
-        TKB_WSTAMP(0);
-        // ---- B. hand the 16 partials to the solver mapping (via this warp's drained FIFO) --------
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 1);
+        // ---- hand the 16 partials to the merge mapping (via this warp's drained FIFO) --------
         cp_async_wait_all();
         __syncwarp();
 #pragma unroll
@@ -393,36 +379,12 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 if (DO_V) my_partV[o] = make_float2(vmax[j][q], __int_as_float(vsel[j][q]));
                 if (DO_L) my_partL[o] = make_float2(lM[j][q], lS[j][q]);
             }
-        // ---- solver set-up that does not depend on the other warps: done BEFORE the barrier ---------------
-        // Solver phases are branch-free: coefficients that must not act (rows at or below a column, rows or
-        // columns beyond T) are -inf, so their pushes leave (best, sel) / (M, S) untouched.
-        const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
-        const bool active = x < T;
-        const bool has_next = nr > 0;  // a later block exists: the top column can skip into row x0+BX
-        const float s_d = park[threadIdx.x], s_eta = park[NT + threadIdx.x];
-        float sreg[BX];  // my column of the diagonal block (log2 domain for the log-sum warps)
-        float u0, u1;    // Viterbi: relu(d), unused | log-sum: softplus(d)*log2e, eta*log2e
-        if (!s_is_lse) {
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagS[(sn * BX + r) * BX + c] : -INFINITY;
-            u0 = relu_mask(s_d);
-            u1 = 0.0f;
-        } else {
-#pragma unroll
-            for (int r = 1; r < BX; ++r) sreg[r] = (r > c) ? diagL[(sn * BX + r) * BX + c] : -INFINITY;
-            {  // softplus(d)*log2e = max(d2,0) + log2(1 + 2^-|d2|), d2 = d*log2e
-                const float d2 = s_d * kLog2e;
-                u0 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));
-            }
-            u1 = s_eta * kLog2e;
-        }
-        TKB_STAMP(1);
-        TKB_WSTAMP(1);
         __syncthreads();
-
-        const float qnext = qtop[(s_is_lse ? 8 : 0) + sn];
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 2);
+        const int c = lane;
+        unsigned long long *dst =
+            p.part + ((((size_t)g * nb + J) * 2 + (s_is_lse ? 1 : 0)) * NG + sn) * (BX * 2) + 2 * c;
         if (!s_is_lse && DO_V) {
-            // ================= Viterbi: (max,+), bit-exact fp32 =================================
             // branch-free 16-way merge: the maximum, then among the partials that attain it the row the
             // reference's candidate order prefers (BACKWARD: smallest y, FORWARD: largest y).  Empty partials
             // are (-inf, -1); (unsigned)-1 is the largest unsigned, so they never win the min.
@@ -437,7 +399,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             float best = pv[0];
 #pragma unroll
             for (int w = 1; w < NW; ++w) best = fmaxf(best, pv[w]);
-            int bsel;  // mirrored y of the best interval so far, -1 = none / skip
+            int bsel;
             if (DIR == TKB_BACKWARD) {
                 unsigned m = 0xffffffffu;
 #pragma unroll
@@ -449,95 +411,310 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 for (int w = 0; w < NW; ++w) m = max(m, pv[w] == best ? ps[w] : -1);
                 bsel = m;
             }
-            const float dr = u0;
-            // terminal column: no candidates, q = S*(S>0)  (-0 + dr reproduces the reference's signed zero)
-            if (x == T - 1) best = -0.0f;
-            // the skip out of the top column: candidate 0 of the reference, so it wins every tie
-            if (has_next && c == BX - 1) {
-                const float xk = qnext + s_eta;
-                bsel = (xk >= best) ? -1 : bsel;
-                best = fmaxf(best, xk);
-            }
-            TKB_STAMP(3);
-            TKB_WSTAMP_DEP(4, best);
-            // ---- D. diagonal solve: value chain = FADD -> SHFL -> FADD -> FMNMX ------------------
-            float qmine = 0.0f;
-#pragma unroll
-            for (int e = BX - 1; e >= 1; --e) {
-                const float qfin = best + dr;
-                const float qb = __shfl_sync(kFull, qfin, e);
-                qmine = (c == e) ? qfin : qmine;
-                const float xi = qb + sreg[e];                              // -inf for lanes c >= e
-                const float xk = (c == e - 1) ? qb + s_eta : -INFINITY;    // skip x -> x+1
-                const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best) : (xi > best);
-                const float b1 = fmaxf(best, xi);
-                bsel = tk ? x0 + e : bsel;
-                bsel = (xk >= b1) ? -1 : bsel;
-                best = fmaxf(b1, xk);
-                if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active)
-                    publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
-            }
-            qmine = (c == 0) ? best + dr : qmine;
-            if (c < PB && active) publish(s_mbox + (size_t)x * p.Npad, qmine, epoch);
-            TKB_STAMP(4);
-            TKB_WSTAMP(5);
-            if (active && s_nok) {
-                const int osel = bsel < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel : T - 1 - bsel);
-                p.code[(size_t)(n0 + sn) * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
-                if (p.outv) p.outv[(size_t)pos * N + n0 + sn] = qmine;
-            }
+            publish(dst, best, epoch);
+            publish(dst + 1, __int_as_float(bsel), epoch);
         } else if (s_is_lse && DO_L) {
-            // ================= log-sum: (logsumexp,+) in the log2 domain, (M, S) pairs ===============
             float M = -FLT_MAX, S = 0.0f;
-            {
-                float m[NW], s[NW];
+            float m[NW], s[NW];
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const float2 e =
-                        reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
-                    m[w] = e.x;
-                    s[w] = e.y;
-                    M = fmaxf(M, e.x);
-                }
+            for (int w = 0; w < NW; ++w) {
+                const float2 e =
+                    reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
+                m[w] = e.x;
+                s[w] = e.y;
+                M = fmaxf(M, e.x);
+            }
 #pragma unroll
-                for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
-            }
-            const float sp2 = u0, eta2 = u1;
-            if (x == T - 1) {  // terminal column: value = softplus(S[T-1,T-1])
-                M = 0.0f;
-                S = 1.0f;
-            }
-            if (has_next && c == BX - 1) lse_push(M, S, qnext + eta2, 1.0f);  // skip out of the top column
-            TKB_WSTAMP_DEP(4, S);
-            // ---- D. diagonal solve: broadcast (M + sp2, S) of lane e, push to every lane (no-op for c >= e)
-#pragma unroll
-            for (int e = BX - 1; e >= 1; --e) {
-                const float Mb = __shfl_sync(kFull, M + sp2, e);
-                const float sb = __shfl_sync(kFull, S, e);
-                lse_push(M, S, Mb + sreg[e], sb);
-                if ((e & (PB - 1)) == 0 && c >= e && c < e + PB && active) {
-                    const float v2 = (M + sp2) + lg2f(S);
-                    publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
-                    if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
-                }
-            }
-            if (c < PB && active) {
-                const float v2 = (M + sp2) + lg2f(S);
-                publish(s_mbox + (size_t)x * p.Npad, v2, epoch);
-                if (s_nok && p.outl) p.outl[(size_t)pos * N + n0 + sn] = v2 * kLn2;
-            }
-            TKB_WSTAMP(5);
+            for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
+            publish(dst, M, epoch);
+            publish(dst + 1, S, epoch);
         }
-        __syncthreads();  // partials (in the FIFOs), diagS and qtop are reused by the next owned block
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 3);
+        __syncthreads();  // the partials live in the FIFOs the next owned block refills
     }
+}
+
+// =================================================================================================
+// SOLVER: the chain of NQ tracks, from the last position to the first, in one SM
+// =================================================================================================
+template <int DIR, int ALIGN, int MODE>
+__device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char *smem_raw, int g, int qd) {
+    constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
+    constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, N = p.N;
+    const int nb = (T + BX - 1) / BX;
+    const int n0 = g * NG + qd * NQ;           // first track of this solver
+    const int nvalid = min(max(N - n0, 0), NQ);  // chain warps with a real track
+    const unsigned epoch = p.epoch;
+    const unsigned band_s = smem_u32(smem_raw);
+    const unsigned full_s = band_s + (unsigned)(NBAND * kBandBytes);  // + slot*8
+    const unsigned empty_s = full_s + NBAND * 8;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NBAND; ++s) {
+            mbar_init(full_s + s * 8, NLW * 32);
+            mbar_init(empty_s + s * 8, nvalid);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (nvalid == 0) return;
+
+    if (warp >= NCW && warp < NCW + NLW) {
+        // ---------------- loader warps: keep the ring of row bands filled ----------------------------
+        // band of row block j: rows y = 32j .. 32j+31, columns x = 32(j-ND) .. 32j+31, this solver's NQ tracks;
+        // chunk (e, cc) -> band + (e*BANDCOLS + cc)*16.  Chunks above the diagonal, left of column 0 or below
+        // row T-1 are never read and not fetched.
+        const int lt = threadIdx.x - NCW * 32;
+        const int nbytes = nvalid * 4;
+        for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
+            const int slot = it % NBAND;
+            if (it >= NBAND) mbar_wait(empty_s + slot * 8, ((it / NBAND) - 1) & 1, p.status);
+            const int y0 = j * BX, xlo = (j - ND) * BX;
+            const unsigned dst0 = band_s + (unsigned)(slot * kBandBytes);
+            for (int i = lt; i < BX * BANDCOLS; i += NLW * 32) {
+                const int e = i / BANDCOLS, cc = i - e * BANDCOLS;
+                const int y = y0 + e, x = xlo + cc;
+                if (x < 0 || x > y || y >= T) continue;
+                const float *src = p.Sbase + (long long)x * p.sx + (long long)y * p.sy + n0;
+                const unsigned dst = dst0 + (unsigned)i * 16u;
+                if (ALIGN == 16) {
+                    cp_async16_s(dst, src, nbytes);
+                } else if (ALIGN == 8) {
+                    cp_async8_s(dst, src, nvalid > 0 ? 8 : 0);
+                    if (nvalid > 2) cp_async8_s(dst + 8, src + 2, 8);
+                } else {
+                    for (int q = 0; q < nvalid; ++q) cp_async4_s(dst + q * 4, src + q, 4);
+                }
+            }
+            mbar_arrive_cp_async(full_s + slot * 8);
+        }
+        cp_async_wait_all();
+        return;
+    }
+    if (warp >= nvalid) return;  // spare warps, and chain warps without a real track
+
+    // ---------------- chain warp: track n, lane = column ---------------------------------------------
+    const int tr = warp;
+    const int n = n0 + tr;
+    const int c = lane;
+    unsigned long long *mV = p.mbox + n;                           // + y * Npad
+    unsigned long long *mL = p.mbox + (size_t)T * p.Npad + n;
+    const int ptrk = qd * NQ + tr;  // track inside the group
+    // accumulators: [0] the block on the chain, [d] the block d below it
+    float best[ND + 1], lM[ND + 1], lS[ND + 1];
+    int bsel[ND + 1];
+#pragma unroll
+    for (int d = 0; d <= ND; ++d) {
+        best[d] = -INFINITY;
+        bsel[d] = -1;
+        lM[d] = -FLT_MAX;
+        lS[d] = 0.0f;
+    }
+    // unary terms of my column in the block on the chain, and (prefetched) in the next one
+    auto load_unary = [&](int j, float &d_out, float &e_out) {
+        const int x = j * BX + c;
+        d_out = 0.0f;
+        e_out = 0.0f;
+        if (j >= 0 && x < T) {
+            d_out = __ldg(p.Sbase + (long long)x * (p.sx + p.sy) + n);
+            if (x < T - 1) e_out = __ldg(p.etabase + (long long)x * p.se + n);
+        }
+    };
+    float nx_d, nx_eta;
+    load_unary(nb - 1, nx_d, nx_eta);
+    float qtopV = 0.0f, qtopM = 0.0f, qtopS = 0.0f;  // row 32(j+1) (the row right above column 31), broadcast
+    // far partial of the NEXT block, fetched while the chain is still in this one
+    unsigned long long fw[4] = {0, 0, 0, 0};
+    const unsigned long long *fsrc = nullptr;
+    auto far_fetch = [&](int jn) {
+        if (jn < 0 || jn > nb - ND - 2) return;
+        fsrc = p.part + ((((size_t)g * nb + jn) * 2) * NG + ptrk) * (BX * 2) + 2 * c;
+        if (DO_V) {
+            fw[0] = ld_relaxed_u64(fsrc);
+            fw[1] = ld_relaxed_u64(fsrc + 1);
+        }
+        if (DO_L) {
+            fw[2] = ld_relaxed_u64(fsrc + (size_t)NG * BX * 2);
+            fw[3] = ld_relaxed_u64(fsrc + (size_t)NG * BX * 2 + 1);
+        }
+    };
+    const float *bands = reinterpret_cast<const float *>(smem_raw);
+
+    for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
+        const int slot = it % NBAND;
+        const int x0 = j * BX, x = x0 + c;
+        const int ncols = min(BX, T - x0);
+        const bool active = x < T;
+        const float s_d = nx_d, s_eta = nx_eta;
+        load_unary(j - 1, nx_d, nx_eta);
+        const float dr = relu_mask(s_d);
+        float sp2 = 0.0f, eta2 = 0.0f;
+        if (DO_L) {
+            const float d2 = s_d * kLog2e;
+            sp2 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));  // softplus(d)*log2e
+            eta2 = s_eta * kLog2e;
+        }
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 0);
+        // ---- far partial of this block (rows of blocks > j+ND), written by the owning helper -------------
+        if (j <= nb - ND - 2) {
+            if (DO_V) {
+                if ((unsigned)(fw[0] >> 32) != epoch) fw[0] = poll_slow<0>(fsrc, epoch, p.status);
+                if ((unsigned)(fw[1] >> 32) != epoch) fw[1] = poll_slow<0>(fsrc + 1, epoch, p.status);
+                const float fv = __uint_as_float((unsigned)fw[0]);
+                const int fs = (int)(unsigned)fw[1];
+                // far rows are larger y than anything accumulated so far: BACKWARD prefers the smaller y on ties
+                const bool tk = (DIR == TKB_BACKWARD) ? (fv > best[0]) : (fv >= best[0]);
+                bsel[0] = tk ? fs : bsel[0];
+                best[0] = fmaxf(best[0], fv);
+            }
+            if (DO_L) {
+                const unsigned long long *srcL = fsrc + (size_t)NG * BX * 2;
+                if ((unsigned)(fw[2] >> 32) != epoch) fw[2] = poll_slow<0>(srcL, epoch, p.status);
+                if ((unsigned)(fw[3] >> 32) != epoch) fw[3] = poll_slow<0>(srcL + 1, epoch, p.status);
+                lse_push(lM[0], lS[0], __uint_as_float((unsigned)fw[2]), __uint_as_float((unsigned)fw[3]));
+            }
+        }
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 1);
+        // ---- the skip out of the top column into row 32(j+1): candidate 0 of the reference, wins every tie ----
+        if (j < nb - 1) {
+            if (DO_V) {
+                const float xk = (c == BX - 1) ? qtopV + s_eta : -INFINITY;
+                bsel[0] = (xk >= best[0]) ? -1 : bsel[0];
+                best[0] = fmaxf(best[0], xk);
+            }
+            if (DO_L) lse_push(lM[0], lS[0], (c == BX - 1) ? qtopM + eta2 : -INFINITY, qtopS);
+        }
+        if (x == T - 1) {  // terminal column: no candidates; q = S*(S>0) (-0 + dr keeps the reference's signed zero)
+            best[0] = -0.0f;
+            bsel[0] = -1;
+            lM[0] = 0.0f;
+            lS[0] = 1.0f;
+        }
+        if (DO_L && lS[0] > 0.0f) {  // renormalise: S restarts at 1 in every block (it at most doubles per step)
+            lM[0] += lg2f(lS[0]);
+            lS[0] = 1.0f;
+        }
+        // ---- wait for the row band ------------------------------------------------------------------
+        mbar_wait(full_s + slot * 8, (it / NBAND) & 1, p.status);
+        // my column in the diagonal tile is band column ND*32 + c; in the tile d blocks below, (ND-d)*32 + c
+        const float *colp = bands + (size_t)slot * (kBandBytes / 4) + c * NQ + tr;
+        // log-sum: the skip x -> x+1 folded into the coefficient of the row right above my column
+        float comb = -INFINITY;
+        if (DO_L && c + 1 < ncols) {
+            const float spv = colp[((c + 1) * BANDCOLS + ND * BX) * NQ] * kLog2e;
+            comb = fmaxf(spv, eta2) + lg2f(1.0f + ex2f(-fabsf(spv - eta2)));
+        }
+        // ---- one chain step: row e of this block is final in lane e; broadcast it and push it -----------
+        auto step = [&](const int e) {
+            const int y = x0 + e;
+            const float *rowp = colp + (size_t)e * (BANDCOLS * NQ);
+            float sv[ND + 1];
+#pragma unroll
+            for (int d = 0; d <= ND; ++d) sv[d] = rowp[(ND - d) * BX * NQ];
+            const bool below = c < e;
+            if (DO_V) {
+                const float qb = __shfl_sync(kFull, best[0] + dr, e);
+                if (e == 0) qtopV = qb;
+                {
+                    const float xi = below ? qb + sv[0] : -INFINITY;
+                    const float xk = (c == e - 1) ? qb + s_eta : -INFINITY;
+                    const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best[0]) : (xi > best[0]);
+                    const float b1 = fmaxf(best[0], xi);
+                    bsel[0] = tk ? y : bsel[0];
+                    bsel[0] = (xk >= b1) ? -1 : bsel[0];
+                    best[0] = fmaxf(b1, xk);
+                }
+#pragma unroll
+                for (int d = 1; d <= ND; ++d) {
+                    const float xi = qb + sv[d];
+                    const bool tk = (DIR == TKB_BACKWARD) ? (xi >= best[d]) : (xi > best[d]);
+                    bsel[d] = tk ? y : bsel[d];
+                    best[d] = fmaxf(best[d], xi);
+                }
+            }
+            if (DO_L) {
+                const float Mb = __shfl_sync(kFull, lM[0] + sp2, e);
+                const float sb = __shfl_sync(kFull, lS[0], e);
+                if (e == 0) {
+                    qtopM = Mb;
+                    qtopS = sb;
+                }
+                const float coef = (c == e - 1) ? comb : (below ? sv[0] * kLog2e : -INFINITY);
+                lse_push(lM[0], lS[0], Mb + coef, sb);
+#pragma unroll
+                for (int d = 1; d <= ND; ++d) lse_push(lM[d], lS[d], fmaf(sv[d], kLog2e, Mb), sb);
+            }
+        };
+        // rows 8*e8 .. 8*e8+7 are final in their lanes: publish them and write the tables
+        auto publish_batch = [&](const int e8) {
+            if (c >= e8 * PB && c < e8 * PB + PB && active) {
+                const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
+                if (DO_V) {
+                    const float qfin = best[0] + dr;
+                    publish(mV + (size_t)x * p.Npad, qfin, epoch);
+                    const int osel = bsel[0] < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel[0] : T - 1 - bsel[0]);
+                    p.code[(size_t)n * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
+                    if (p.outv) p.outv[(size_t)pos * N + n] = qfin;
+                }
+                if (DO_L) {
+                    const float v2 = (lM[0] + sp2) + lg2f(lS[0]);
+                    publish(mL + (size_t)x * p.Npad, v2, epoch);
+                    if (p.outl) p.outl[(size_t)pos * N + n] = v2 * kLn2;
+                }
+            }
+        };
+        if (ncols == BX) {
+#pragma unroll
+            for (int e8 = BX / PB - 1; e8 >= 0; --e8) {
+                if (e8 == 0) far_fetch(j - 1);
+#pragma unroll
+                for (int i = PB - 1; i >= 0; --i) step(e8 * PB + i);
+                publish_batch(e8);
+            }
+        } else {  // the ragged top block
+            far_fetch(j - 1);
+            for (int e8 = (ncols - 1) >> 3; e8 >= 0; --e8) {
+                for (int e = min(ncols - 1, e8 * PB + PB - 1); e >= e8 * PB; --e) step(e);
+                publish_batch(e8);
+            }
+        }
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 2);
+        // ---- next block: release the band, shift the accumulators ------------------------------------------
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_s + slot * 8);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            best[d] = best[d + 1];
+            bsel[d] = bsel[d + 1];
+            lM[d] = lM[d + 1];
+            lS[d] = lS[d + 1];
+        }
+        best[ND] = -INFINITY;
+        bsel[ND] = -1;
+        lM[ND] = -FLT_MAX;
+        lS[ND] = 0.0f;
+    }
+}
+
+template <int DIR, int ALIGN, int MODE>
+__global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int per = 2 + p.H;
+    const int g = p.g0 + (int)blockIdx.x / per, role = (int)blockIdx.x % per;
+    if (role < 2)
+        solver_role<DIR, ALIGN, MODE>(p, smem_raw, g, role);
+    else
+        helper_role<DIR, ALIGN, MODE>(p, smem_raw, g, role - 2);
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int DIR, bool A16, int MODE>
+template <int DIR, int ALIGN, int MODE>
 static int launch_one(const SweepParams &p, int grid, cudaStream_t stream) {
-    auto kern = sweep_kernel<DIR, A16, MODE>;
+    auto kern = sweep_kernel<DIR, ALIGN, MODE>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         TKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
@@ -549,12 +726,21 @@ static int launch_one(const SweepParams &p, int grid, cudaStream_t stream) {
     return 0;
 }
 
-template <int DIR, bool A16>
+template <int DIR, int ALIGN>
 static int launch_mode(int mode, const SweepParams &p, int grid, cudaStream_t stream) {
     switch (mode) {
-        case TKB_SWEEP_VITERBI: return launch_one<DIR, A16, TKB_SWEEP_VITERBI>(p, grid, stream);
-        case TKB_SWEEP_LOGSUM: return launch_one<DIR, A16, TKB_SWEEP_LOGSUM>(p, grid, stream);
-        default: return launch_one<DIR, A16, TKB_SWEEP_VITERBI | TKB_SWEEP_LOGSUM>(p, grid, stream);
+        case TKB_SWEEP_VITERBI: return launch_one<DIR, ALIGN, TKB_SWEEP_VITERBI>(p, grid, stream);
+        case TKB_SWEEP_LOGSUM: return launch_one<DIR, ALIGN, TKB_SWEEP_LOGSUM>(p, grid, stream);
+        default: return launch_one<DIR, ALIGN, TKB_SWEEP_VITERBI | TKB_SWEEP_LOGSUM>(p, grid, stream);
+    }
+}
+
+template <int DIR>
+static int launch_align(int align, int mode, const SweepParams &p, int grid, cudaStream_t stream) {
+    switch (align) {
+        case 16: return launch_mode<DIR, 16>(mode, p, grid, stream);
+        case 8: return launch_mode<DIR, 8>(mode, p, grid, stream);
+        default: return launch_mode<DIR, 4>(mode, p, grid, stream);
     }
 }
 
@@ -568,6 +754,22 @@ static int num_sms() {
     }
     return g_num_sms;
 }
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TKB_SWEEP_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+static size_t mailbox_bytes(int T, int N) {
+    const size_t npad = (size_t)((N + NG - 1) / NG) * NG;
+    return 2 * (size_t)T * npad * sizeof(unsigned long long);
+}
+static size_t partial_bytes(int T, int N) {
+    const size_t G = (size_t)((N + NG - 1) / NG), nb = (size_t)((T + BX - 1) / BX);
+    return G * nb * 2 * NG * BX * 2 * sizeof(unsigned long long);
+}
 
 }  // namespace tkb
 
@@ -575,13 +777,17 @@ using namespace tkb;
 
 extern "C" size_t tkb_sweep_workspace_bytes(int T, int N) {
     if (T < 1 || N < 1) return 0;
-    const size_t npad = (size_t)((N + NG - 1) / NG) * NG;
-    return kHeaderBytes + 2 * (size_t)T * npad * sizeof(unsigned long long);
+    const size_t v2 = kHeaderBytes + mailbox_bytes(T, N) + partial_bytes(T, N);
+    const size_t v1 = sweep_workspace_bytes_v1(T, N);
+    return v2 > v1 ? v2 : v1;
 }
 
 extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
                                  void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit,
                                  float *out_lse, void *stream_) {
+    if (use_v1())
+        return semicrf_sweep_v1(score, noise, T, N, direction, flags, workspace, epoch, out_code, out_vit, out_lse,
+                                stream_);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!score || !workspace || T < 1 || N < 1 || (T > 1 && !noise) || epoch == 0 ||
         (direction != TKB_BACKWARD && direction != TKB_FORWARD) ||
@@ -592,7 +798,7 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
         return TKB_EINVAL;
     }
     const int sms = num_sms();
-    if (sms <= 0) {
+    if (sms < 3) {
         set_error("tkb_semicrf_sweep: no CUDA device");
         return TKB_ENODEV;
     }
@@ -605,6 +811,8 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
     p.epoch = epoch;
     p.status = reinterpret_cast<int *>(workspace);
     p.mbox = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(workspace) + kHeaderBytes);
+    p.part = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(workspace) + kHeaderBytes +
+                                                    mailbox_bytes(T, N));
     p.code = out_code;
     p.outv = out_vit;
     p.outl = out_lse;
@@ -622,24 +830,22 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
         p.etabase = noise ? noise + (long long)(T - 2) * N : nullptr;  // skip weight of x is noise[T-2-x]
         p.se = -(long long)N;
     }
-    const bool a16 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(score) & 15) == 0);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(score);
+    const int align = (N % 4 == 0 && (addr & 15) == 0) ? 16 : ((N % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
     const int nb = (T + BX - 1) / BX;
-    // groups are independent pipelines; split them over launches if there are more groups than SMs
-    for (int g0 = 0; g0 < p.G; g0 += sms) {
-        const int gcount = (p.G - g0) < sms ? (p.G - g0) : sms;
-        int K = sms / gcount;
-        if (K > nb) K = nb;
-        if (K < 1) K = 1;
+    const int hmax = nb - ND - 1 > 1 ? nb - ND - 1 : 1;  // column blocks that have a far field at all
+    // groups are independent pipelines; split them over launches if there are more groups than SMs / 3
+    const int gmax = sms / 3;
+    for (int g0 = 0; g0 < p.G; g0 += gmax) {
+        const int gcount = (p.G - g0) < gmax ? (p.G - g0) : gmax;
+        int H = sms / gcount - 2;
+        if (H > hmax) H = hmax;
+        if (H < 1) H = 1;
         p.g0 = g0;
-        p.K = K;
-        const int grid = gcount * K;
-        int rc;
-        if (direction == TKB_BACKWARD)
-            rc = a16 ? launch_mode<TKB_BACKWARD, true>(flags, p, grid, stream)
-                     : launch_mode<TKB_BACKWARD, false>(flags, p, grid, stream);
-        else
-            rc = a16 ? launch_mode<TKB_FORWARD, true>(flags, p, grid, stream)
-                     : launch_mode<TKB_FORWARD, false>(flags, p, grid, stream);
+        p.H = H;
+        const int grid = gcount * (2 + H);
+        const int rc = direction == TKB_BACKWARD ? launch_align<TKB_BACKWARD>(align, flags, p, grid, stream)
+                                                 : launch_align<TKB_FORWARD>(align, flags, p, grid, stream);
         if (rc != 0) return rc;
     }
     return 0;
