@@ -22,44 +22,58 @@ L = _lib.load()
 score, noise = make_inputs("randn", T, N, 1234)
 s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
 grid_max = 148
-tl = torch.zeros((grid_max * 64 * 4,), dtype=torch.int64, device="cuda")
+tl = torch.zeros((grid_max * 64 * 8,), dtype=torch.int64, device="cuda")
 L.tkb_debug_set_timeline.argtypes = [ctypes.c_void_p]
 L.tkb_debug_set_timeline(tl.data_ptr())
+import os  # noqa: E402
 for _ in range(3):
+    tl.zero_()
+    *_, ws = sweep(s, z, BACKWARD, flags)
+    torch.cuda.synchronize()
+if os.environ.get("TKB_REPLAY") == "1":  # same epoch again: nobody waits (free-running roles)
+    ws.epoch -= 1
     tl.zero_()
     sweep(s, z, BACKWARD, flags)
     torch.cuda.synchronize()
-t = tl.cpu().numpy().astype(np.float64).reshape(grid_max, 64, 4)
+    print("REPLAY launch (same epoch, no waits)")
+raw = tl.cpu().numpy().astype(np.float64).reshape(grid_max, 64, 8)
+t = raw[:, :, :4].copy()
 G = (N + 7) // 8
 nb = (T + 31) // 32
-H = max(1, min(148 // G - 2, nb - ND - 1))
-per = 2 + H
-t0 = t[t > 0].min()
+NSOLV = 4
+F = min(nb, 16)
+H = max(1, min((148 - F) // G - NSOLV, nb - ND - 1))
+per = NSOLV + H
+t0 = t[:, :, :3][t[:, :, :3] > 0].min()
 print(f"T={T} N={N} G={G} H={H} nb={nb}; kernel span {(t.max() - t0) / 1e3:.1f} us")
-for g in (0, G // 2):
-    sol = (t[g * per] - t0) / 1e3  # solver of quad 0: [block it][start, far partial merged, chain done]
-    print(f"group {g}: solver blocks (us since kernel start): start | wait for far partial | chain | block time")
-    prev = None
-    for it in range(min(nb, 64)):
-        st, mg, dn = sol[it, 0], sol[it, 1], sol[it, 2]
-        j = nb - 1 - it
-        own = None
-        if j <= nb - ND - 2:
-            h = (nb - ND - 2 - j) % H
-            idx = (nb - ND - 2 - j) // H
-            if idx < 64:
-                own = (t[g * per + 2 + h, idx] - t0) / 1e3  # helper: start, far done, merged-sync, published
-        line = f"  j={j:3d} start {st:7.2f} | wait {mg - st:5.2f} | chain {dn - mg:5.2f} | step {0.0 if prev is None else st - prev:5.2f}"
-        if own is not None:
-            line += f" || helper start {own[0]:7.2f} far_done {own[1]:7.2f} published {own[3]:7.2f} (slack {st - own[3]:6.2f})"
-        print(line)
-        prev = st
 hs = []
 for g in range(G):
     for h in range(H):
-        a = t[g * per + 2 + h]
+        a = t[g * per + NSOLV + h]
         m = a[:, 0] > 0
         if m.any():
             hs.append(((a[m, 3] - a[m, 0]).sum() / 1e3, (a[m, 1] - a[m, 0]).sum() / 1e3))
 hs = np.array(hs)
 print(f"helpers: busy (start->published) mean {hs[:, 0].mean():.1f} us, max {hs[:, 0].max():.1f}; far-field part mean {hs[:, 1].mean():.1f}")
+
+# solver clock64 stamps of the Viterbi chain warp of track 0 (cycles): 3 block start, 4 prep slot ready + far partial merged,
+# 5 band ready, 7 chain done
+for g in (0, G // 2):
+    c = raw[g * per]
+    its = [it for it in range(3, min(nb, 64) - 1)]
+    prep_wait = np.mean([c[it, 4] - c[it, 3] for it in its])
+    band_wait = np.mean([c[it, 5] - c[it, 4] for it in its])
+    chain = np.mean([c[it, 7] - c[it, 5] for it in its])
+    block = np.mean([c[it + 1, 3] - c[it, 3] for it in its])
+    print(f"group {g} V chain cycles per block: {block:.0f} | prep wait+merge {prep_wait:.0f} | band wait {band_wait:.0f} | "
+          f"32 columns {chain:.0f} ({chain / 32:.1f}/column) | rest {block - prep_wait - band_wait - chain:.0f}")
+    print("   V band wait per block:", " ".join(f"{int(c[it, 5] - c[it, 4])}" for it in range(min(nb, 64))))
+    print("   V prep wait per block:", " ".join(f"{int(c[it, 4] - c[it, 3])}" for it in range(min(nb, 64))))
+    print("   V columns  per block:", " ".join(f"{int(c[it, 7] - c[it, 5])}" for it in range(min(nb, 64))))
+    if flags & 2:
+        prep_wait = np.mean([c[it, 1] - c[it, 0] for it in its])
+        band_wait = np.mean([c[it, 2] - c[it, 1] for it in its])
+        chain = np.mean([c[it, 6] - c[it, 2] for it in its])
+        block = np.mean([c[it + 1, 0] - c[it, 0] for it in its])
+        print(f"group {g} L chain cycles per block: {block:.0f} | prep wait+merge {prep_wait:.0f} | band wait {band_wait:.0f} | "
+              f"32 columns {chain:.0f} ({chain / 32:.1f}/column) | rest {block - prep_wait - band_wait - chain:.0f}")

@@ -34,8 +34,10 @@ def test_header_symbols_exported(lib):
 def test_version_and_sizes(lib):
     assert lib.tkb_version() == 1
     # header + row mailbox (2 semirings * T * ceil8(N) words) + far partials (groups * blocks * 2 * 8 * 32 * 2 words)
-    assert lib.tkb_sweep_workspace_bytes(2048, 88) == 256 + 2 * 2048 * 88 * 8 + 11 * 64 * 2 * 8 * 32 * 2 * 8
-    assert lib.tkb_sweep_workspace_bytes(10, 9) == 256 + 2 * 10 * 16 * 8 + 2 * 1 * 2 * 8 * 32 * 2 * 8
+    # + band flags + the near-band ring (16 slots * 32 rows * tracks of one launch * 96 columns, fp32)
+    ring = lambda tracks: 256 + 16 * 32 * tracks * 96 * 4
+    assert lib.tkb_sweep_workspace_bytes(2048, 88) == 256 + 2 * 2048 * 88 * 8 + 11 * 64 * 2 * 8 * 32 * 2 * 8 + ring(88)
+    assert lib.tkb_sweep_workspace_bytes(10, 9) == 256 + 2 * 10 * 16 * 8 + 2 * 1 * 2 * 8 * 32 * 2 * 8 + ring(16)
     assert lib.tkb_sweep_workspace_bytes(0, 4) == 0
 
 

@@ -12,12 +12,6 @@ namespace tkb {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);  // records the error, returns (int)e
 
-// first-generation sweep (column blocks round-robin over the CTAs of a group, chain crossing CTAs every block);
-// kept selectable with TKB_SWEEP_V1=1 for A/B timing while the solver/helper kernel replaces it
-size_t sweep_workspace_bytes_v1(int T, int N);
-int semicrf_sweep_v1(const float *score, const float *noise, int T, int N, int direction, int flags, void *workspace,
-                     uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream);
-
 #define TKB_CUDA(call)                                          \
     do {                                                        \
         cudaError_t _e = (call);                                \
