@@ -55,8 +55,11 @@ def run(T, N, kind, seed=7):
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     allok = True
-    for T, N, kind in [(2, 1, "randn"), (5, 3, "randn"), (31, 8, "randn"), (32, 8, "randn"), (33, 8, "randn"),
+    shapes = [(2, 1, "randn"), (5, 3, "randn"), (31, 8, "randn"), (32, 8, "randn"), (33, 8, "randn"),
                        (64, 8, "ties"), (65, 9, "ties"), (100, 4, "model"), (200, 88, "randn"), (256, 90, "ties"),
-                       (512, 88, "randn"), (1024, 88, "randn"), (2048, 88, "randn")]:
+                       (512, 88, "randn"), (691, 90, "model"), (300, 180, "randn"), (1024, 88, "randn"), (2048, 88, "randn")]
+    if len(sys.argv) > 1:
+        shapes = [(int(a.split(",")[0]), int(a.split(",")[1]), a.split(",")[2]) for a in sys.argv[1:]]
+    for T, N, kind in shapes:
         allok &= run(T, N, kind)
     print("ALL OK" if allok else "SOME FAILED")

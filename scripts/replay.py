@@ -4,7 +4,10 @@ A launch that reuses the previous launch's epoch finds every mailbox word and ev
 valid, so nobody ever waits: its duration is max(chain alone, far-field streaming alone) -- which of the two
 bounds the real (dependent) launch.  Results are identical (same values rewritten).
 usage: python scripts/replay.py [T] [N] [flags]"""
+import os
 import sys
+
+os.environ.setdefault("TKB_SWEEP", "strip")  # these diagnostics target the strip design
 
 import torch
 

@@ -2,7 +2,10 @@
 python -c 'from transkun_b200.build import build_timeline; build_timeline()' ; run with
 TKB_LIBRARY=transkun_b200/csrc/libtranskun_b200_timeline.so python scripts/timeline.py [T] [N])."""
 import ctypes
+import os
 import sys
+
+os.environ.setdefault("TKB_SWEEP", "strip")  # these diagnostics target the strip design
 
 import numpy as np
 import torch
@@ -44,22 +47,10 @@ NSOLV = 4
 F = min(nb, 16)
 H = max(1, min((148 - F) // G - NSOLV, nb - ND - 1))
 per = NSOLV + H
-t0 = t[:, :, :3][t[:, :, :3] > 0].min()
-print(f"T={T} N={N} G={G} H={H} nb={nb}; kernel span {(t.max() - t0) / 1e3:.1f} us")
-hs = []
-for g in range(G):
-    for h in range(H):
-        a = t[g * per + NSOLV + h]
-        m = a[:, 0] > 0
-        if m.any():
-            hs.append(((a[m, 3] - a[m, 0]).sum() / 1e3, (a[m, 1] - a[m, 0]).sum() / 1e3))
-hs = np.array(hs)
-print(f"helpers: busy (start->published) mean {hs[:, 0].mean():.1f} us, max {hs[:, 0].max():.1f}; far-field part mean {hs[:, 1].mean():.1f}")
-
 # solver clock64 stamps of the Viterbi chain warp of track 0 (cycles): 3 block start, 4 prep slot ready + far partial merged,
 # 5 band ready, 7 chain done
 for g in (0, G // 2):
-    c = raw[g * per]
+    c = raw[g * NSOLV]
     its = [it for it in range(3, min(nb, 64) - 1)]
     prep_wait = np.mean([c[it, 4] - c[it, 3] for it in its])
     band_wait = np.mean([c[it, 5] - c[it, 4] for it in its])
@@ -77,3 +68,28 @@ for g in (0, G // 2):
         block = np.mean([c[it + 1, 0] - c[it, 0] for it in its])
         print(f"group {g} L chain cycles per block: {block:.0f} | prep wait+merge {prep_wait:.0f} | band wait {band_wait:.0f} | "
               f"32 columns {chain:.0f} ({chain / 32:.1f}/column) | rest {block - prep_wait - band_wait - chain:.0f}")
+
+# strip CTAs (globaltimer ns): per unit 0 start, 1 near tiles done, 2 far field done, 3 partial published
+nsolv = ((N + 1) // 2 + 3) // 4 * 4
+nstrip = 148 - nsolv
+K = 8
+tt = raw[nsolv:nsolv + nstrip, :, :4]
+valid = tt[:, :, 3] > 0
+t00 = tt[:, :, 0][tt[:, :, 0] > 0].min()
+near = (tt[:, :, 1] - tt[:, :, 0])[valid] / 1e3
+far = (tt[:, :, 2] - tt[:, :, 1])[valid] / 1e3
+pub = (tt[:, :, 3] - tt[:, :, 2])[valid] / 1e3
+print(f"strips: {nstrip} CTAs, {valid.sum()} units with a far field; per unit: near {near.mean():.2f} us, far {far.mean():.2f} us, "
+      f"partial {pub.mean():.2f} us; last publish at {(tt[:, :, 3].max() - t00) / 1e3:.1f} us")
+for hh in (0, 50, nstrip - 1):
+    line = []
+    for uo in range(8):
+        if tt[hh, uo, 0] <= 0:
+            break
+        u = hh + uo * nstrip
+        J = nb - 1 - u // K
+        R = T - (J * 32 + (ND + 1) * 32)
+        stages = 0 if R < 1 else max(0, (((R + 3) // 4) - (u % K) + K - 1) // K)
+        line.append(f"[J={J} k={u % K} stages={stages}: start {(tt[hh, uo, 0] - t00) / 1e3:.1f} near {(tt[hh, uo, 1] - tt[hh, uo, 0]) / 1e3:.1f} "
+                    f"far {(tt[hh, uo, 2] - tt[hh, uo, 1]) / 1e3:.1f} pub {(tt[hh, uo, 3] - tt[hh, uo, 2]) / 1e3:.1f}]")
+    print(f"  strip {hh}:", " ".join(line))

@@ -33,11 +33,19 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_sizes(lib):
     assert lib.tkb_version() == 1
-    # header + row mailbox (2 semirings * T * ceil8(N) words) + far partials (groups * blocks * 2 * 8 * 32 * 2 words)
-    # + band flags + the near-band ring (16 slots * 32 rows * tracks of one launch * 96 columns, fp32)
-    ring = lambda tracks: 256 + 16 * 32 * tracks * 96 * 4
-    assert lib.tkb_sweep_workspace_bytes(2048, 88) == 256 + 2 * 2048 * 88 * 8 + 11 * 64 * 2 * 8 * 32 * 2 * 8 + ring(88)
-    assert lib.tkb_sweep_workspace_bytes(10, 9) == 256 + 2 * 10 * 16 * 8 + 2 * 1 * 2 * 8 * 32 * 2 * 8 + ring(16)
+    # the workspace serves both sweep designs: the larger of
+    #   solver/helper: header + row mailbox (2 semirings * T * ceil8(N) words) + far partials
+    #   strip        : header + solved rows + block flags + far partials + unit/band flags + near-band ring
+    a256 = lambda x: (x + 255) // 256 * 256
+    def ws(T, N):
+        npad, nb, G = (N + 7) // 8 * 8, (T + 31) // 32, (N + 7) // 8
+        v2 = 256 + 2 * T * npad * 8 + G * nb * 2 * 8 * 32 * 2 * 8
+        strip = (256 + a256(2 * T * npad * 4) + a256(2 * nb * npad * 4) + a256(nb * 8 * 4 * npad * 32 * 4)
+                 + a256(nb * 8 * 2 * 8) + a256(2 * 16 * 3 * 8 * 8) + 16 * min(npad, 176) * 32 * 96 * 4)
+        return max(v2, strip)
+    assert lib.tkb_sweep_workspace_bytes(2048, 88) == ws(2048, 88)
+    assert lib.tkb_sweep_workspace_bytes(10, 9) == ws(10, 9)
+    assert lib.tkb_sweep_workspace_bytes(300, 1200) == ws(300, 1200)
     assert lib.tkb_sweep_workspace_bytes(0, 4) == 0
 
 

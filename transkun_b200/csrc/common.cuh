@@ -12,6 +12,14 @@ namespace tkb {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);  // records the error, returns (int)e
 
+// experimental strip design of the sweep (semicrf_sweep_strip.cu), selected with TKB_SWEEP=strip
+namespace strip {
+size_t workspace_bytes(int T, int N);
+int sweep(const float *score, const float *noise, int T, int N, int direction, int flags, void *workspace,
+          uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream);
+void set_timeline(unsigned long long *buf);
+}  // namespace strip
+
 #define TKB_CUDA(call)                                          \
     do {                                                        \
         cudaError_t _e = (call);                                \
