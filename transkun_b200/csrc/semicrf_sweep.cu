@@ -17,12 +17,14 @@
 // chain inside ONE SM from the first to the last position, and lets every other SM stream the
 // triangle:
 //   * tracks are independent; a GROUP is 8 tracks = one 32-byte sector of the track-innermost layout;
-//   * per group two SOLVER CTAs (4 tracks = 16 bytes each) run the chain: one warp per track, lane =
-//     column of the current 32-column block, V and L semirings interleaved in the same instruction
-//     stream.  A chain step broadcasts the just-finished row with shuffles and pushes it into the
-//     current block (the diagonal tile, on the chain) and into the next ND blocks (off the chain); the
-//     score values come from a shared-memory ring of "row bands" (32 rows x (ND+1)*32 columns x 16 B)
-//     that four loader warps of the same CTA keep filled with cp.async, mbarrier-synchronised;
+//   * per group two SOLVER CTAs (4 tracks = 16 bytes each) run the chain: one warp per track and semiring
+//     (the Viterbi and the log-sum chain of a track sit on the same SMSP, their dependent steps interleave),
+//     lane = column of the current 32-column block.  A chain step broadcasts the just-finished row with
+//     shuffles and pushes it into the current block (the diagonal tile, on the chain) and into the next ND
+//     blocks (off the chain); the score values come from a shared-memory ring of "row bands" (32 rows x
+//     (ND+1)*32 columns x 16 B) that four loader warps of the same CTA keep filled with cp.async,
+//     mbarrier-synchronised; finished rows leave through a shared-memory ring to one publisher warp per
+//     track, which does the global stores (mailbox, back-pointer codes, tables);
 //   * per group H HELPER CTAs own the column blocks round-robin and stream everything further than ND
 //     blocks above the diagonal (the bulk of the bytes): 16 warps, each every 16th pair of rows,
 //     cp.async FIFOs, register accumulators, merged once per block and handed to the solvers as a
@@ -52,6 +54,9 @@ constexpr int NCW = NQ;    // chain warps
 constexpr int NLW = 4;     // loader warps
 constexpr int SLOTS = 4;   // helper: per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
 constexpr int PB = 8;      // rows per publish batch
+#ifndef TKB_FARFETCH_BATCH
+#define TKB_FARFETCH_BATCH 3
+#endif
 
 // helper shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (tagged) | untagged copy.
 // After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
@@ -63,7 +68,11 @@ constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy, same 
 constexpr size_t kHelperSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4;
 // solver shared memory: row bands [NBAND][BX rows][BANDCOLS][NQ tracks] | mbarriers full[NBAND], empty[NBAND]
 constexpr size_t kBandBytes = (size_t)BX * BANDCOLS * NQ * 4;
-constexpr size_t kSolverSmem = (size_t)NBAND * kBandBytes + 2 * NBAND * 8;
+// | publish ring [NCW tracks][2 blocks][BX][2 semirings] 8-byte results | mbarriers pub full[NCW][2 blocks][BX/PB]
+// (eight arrivals each, one outstanding phase), pub empty[NCW][2]
+constexpr size_t kPubBytes = (size_t)NCW * 2 * BX * 2 * 8;
+constexpr size_t kSolverSmem =
+    (size_t)NBAND * kBandBytes + 2 * NBAND * 8 + kPubBytes + NCW * 2 * (BX / PB) * 8 + NCW * 2 * 8;
 constexpr size_t kSweepSmem = kHelperSmem > kSolverSmem ? kHelperSmem : kSolverSmem;
 static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
 static_assert(kSweepSmem <= 227 * 1024, "shared memory budget");
@@ -154,6 +163,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int *st
 }
 __device__ __forceinline__ void cp_async8_s(unsigned saddr, const void *gsrc, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// Chain -> publisher hand-off.  No "memory" clobber on purpose: volatile asm statements keep their mutual order
+// (store, then arrive with release semantics, both by the same lane), while the compiler stays free to move the
+// band reads of the following steps across them.
+__device__ __forceinline__ void sts64_nc(unsigned saddr, unsigned lo, unsigned hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(lo), "r"(hi));
+}
+__device__ __forceinline__ void mbar_arrive_nc(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar));
 }
 __device__ __forceinline__ float lds32(unsigned saddr) {
     float v;
@@ -434,73 +452,26 @@ __device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char 
     }
 }
 
-// =================================================================================================
-// SOLVER: the chain of NQ tracks, from the last position to the first, in one SM
-// =================================================================================================
-template <int DIR, int ALIGN, int MODE>
-__device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char *smem_raw, int g, int qd) {
-    constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
-    constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One chain warp: track n0 + tr, lane = column of the current block, semirings CV / CL.  When a launch computes
+// both, each track has two chain warps (one per semiring) on the same SMSP: their dependent chains interleave.
+struct ChainCtx {
+    unsigned full_s, empty_s, pub_s, pubfull_s, pubempty_s;
+    int g, qd, n0, tr;
+};
+template <int DIR, bool CV, bool CL>
+__device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *smem_raw, const ChainCtx &cx) {
+    constexpr bool DO_V = CV, DO_L = CL;
+    const int lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
     const int nb = (T + BX - 1) / BX;
-    const int n0 = g * NG + qd * NQ;           // first track of this solver
-    const int nvalid = min(max(N - n0, 0), NQ);  // chain warps with a real track
     const unsigned epoch = p.epoch;
-    const unsigned band_s = smem_u32(smem_raw);
-    const unsigned full_s = band_s + (unsigned)(NBAND * kBandBytes);  // + slot*8
-    const unsigned empty_s = full_s + NBAND * 8;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NBAND; ++s) {
-            mbar_init(full_s + s * 8, NLW * 32);
-            mbar_init(empty_s + s * 8, nvalid);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (nvalid == 0) return;
-
-    if (warp >= NCW && warp < NCW + NLW) {
-        // ---------------- loader warps: keep the ring of row bands filled ----------------------------
-        // band of row block j: rows y = 32j .. 32j+31, columns x = 32(j-ND) .. 32j+31, this solver's NQ tracks;
-        // chunk (e, cc) -> band + (e*BANDCOLS + cc)*16.  Chunks above the diagonal, left of column 0 or below
-        // row T-1 are never read and not fetched.
-        const int lt = threadIdx.x - NCW * 32;
-        const int nbytes = nvalid * 4;
-        for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
-            const int slot = it % NBAND;
-            if (it >= NBAND) mbar_wait(empty_s + slot * 8, ((it / NBAND) - 1) & 1, p.status);
-            const int y0 = j * BX, xlo = (j - ND) * BX;
-            const unsigned dst0 = band_s + (unsigned)(slot * kBandBytes);
-            for (int i = lt; i < BX * BANDCOLS; i += NLW * 32) {
-                const int e = i / BANDCOLS, cc = i - e * BANDCOLS;
-                const int y = y0 + e, x = xlo + cc;
-                if (x < 0 || x > y || y >= T) continue;
-                const float *src = p.Sbase + (long long)x * p.sx + (long long)y * p.sy + n0;
-                const unsigned dst = dst0 + (unsigned)i * 16u;
-                if (ALIGN == 16) {
-                    cp_async16_s(dst, src, nbytes);
-                } else if (ALIGN == 8) {
-                    cp_async8_s(dst, src, nvalid > 0 ? 8 : 0);
-                    if (nvalid > 2) cp_async8_s(dst + 8, src + 2, 8);
-                } else {
-                    for (int q = 0; q < nvalid; ++q) cp_async4_s(dst + q * 4, src + q, 4);
-                }
-            }
-            mbar_arrive_cp_async(full_s + slot * 8);
-        }
-        cp_async_wait_all();
-        return;
-    }
-    if (warp >= nvalid) return;  // spare warps, and chain warps without a real track
-
+    const unsigned full_s = cx.full_s, empty_s = cx.empty_s, pub_s = cx.pub_s, pubfull_s = cx.pubfull_s,
+                   pubempty_s = cx.pubempty_s;
+    const int g = cx.g, qd = cx.qd, n0 = cx.n0, tr = cx.tr;
+    (void)N;
     // ---------------- chain warp: track n, lane = column ---------------------------------------------
-    const int tr = warp;
     const int n = n0 + tr;
     const int c = lane;
-    unsigned long long *mV = p.mbox + n;                           // + y * Npad
-    unsigned long long *mL = p.mbox + (size_t)T * p.Npad + n;
     const int ptrk = qd * NQ + tr;  // track inside the group
     // accumulators: [0] the block on the chain, [d] the block d below it
     float best[ND + 1], lM[ND + 1], lS[ND + 1];
@@ -546,7 +517,7 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char 
         const int slot = it % NBAND;
         const int x0 = j * BX, x = x0 + c;
         const int ncols = min(BX, T - x0);
-        const bool active = x < T;
+        if (it >= 2) mbar_wait(pubempty_s + (tr * 2 + (it & 1)) * 8, ((it >> 1) - 1) & 1, p.status);
         const float s_d = nx_d, s_eta = nx_eta;
         load_unary(j - 1, nx_d, nx_eta);
         const float dr = relu_mask(s_d);
@@ -647,28 +618,23 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char 
                 for (int d = 1; d <= ND; ++d) lse_push(lM[d], lS[d], fmaf(sv[d], kLog2e, Mb), sb);
             }
         };
-        // rows 8*e8 .. 8*e8+7 are final in their lanes: publish them and write the tables
+        // rows 8*e8 .. 8*e8+7 are final in their lanes: hand them to the publisher warp of this track
         auto publish_batch = [&](const int e8) {
-            if (c >= e8 * PB && c < e8 * PB + PB && active) {
-                const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
+            if (c >= e8 * PB && c < e8 * PB + PB) {
+                const unsigned dst = pub_s + (unsigned)((((tr * 2 + (it & 1)) * BX + c) * 2) * 8);
                 if (DO_V) {
                     const float qfin = best[0] + dr;
-                    publish(mV + (size_t)x * p.Npad, qfin, epoch);
                     const int osel = bsel[0] < 0 ? -1 : ((DIR == TKB_BACKWARD) ? bsel[0] : T - 1 - bsel[0]);
-                    p.code[(size_t)n * T + pos] = ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u);
-                    if (p.outv) p.outv[(size_t)pos * N + n] = qfin;
+                    sts64_nc(dst, __float_as_uint(qfin), ((unsigned)(osel + 1) << 1) | (s_d > 0.0f ? 1u : 0u));
                 }
-                if (DO_L) {
-                    const float v2 = (lM[0] + sp2) + lg2f(lS[0]);
-                    publish(mL + (size_t)x * p.Npad, v2, epoch);
-                    if (p.outl) p.outl[(size_t)pos * N + n] = v2 * kLn2;
-                }
+                if (DO_L) sts64_nc(dst + 8, __float_as_uint(lM[0] + sp2), __float_as_uint(lS[0]));
+                mbar_arrive_nc(pubfull_s + (unsigned)(((tr * 2 + (it & 1)) * (BX / PB) + e8) * 8));
             }
         };
         if (ncols == BX) {
 #pragma unroll
             for (int e8 = BX / PB - 1; e8 >= 0; --e8) {
-                if (e8 == 0) far_fetch(j - 1);
+                if (e8 == TKB_FARFETCH_BATCH) far_fetch(j - 1);
 #pragma unroll
                 for (int i = PB - 1; i >= 0; --i) step(e8 * PB + i);
                 publish_batch(e8);
@@ -695,6 +661,133 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char 
         bsel[ND] = -1;
         lM[ND] = -FLT_MAX;
         lS[ND] = 0.0f;
+    }
+}
+
+// =================================================================================================
+// SOLVER: the chain of NQ tracks, from the last position to the first, in one SM
+// =================================================================================================
+template <int DIR, int ALIGN, int MODE>
+__device__ __forceinline__ void solver_role(const SweepParams &p, unsigned char *smem_raw, int g, int qd) {
+    constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
+    constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, N = p.N;
+    const int nb = (T + BX - 1) / BX;
+    const int n0 = g * NG + qd * NQ;           // first track of this solver
+    const int nvalid = min(max(N - n0, 0), NQ);  // chain warps with a real track
+    const unsigned epoch = p.epoch;
+    const unsigned band_s = smem_u32(smem_raw);
+    const unsigned full_s = band_s + (unsigned)(NBAND * kBandBytes);  // + slot*8
+    const unsigned empty_s = full_s + NBAND * 8;
+    const unsigned pub_s = empty_s + NBAND * 8;                      // [tr][block parity][c][kind] 8 bytes
+    const unsigned pubfull_s = pub_s + (unsigned)kPubBytes;          // [tr][block parity][batch]
+    const unsigned pubempty_s = pubfull_s + NCW * 2 * (BX / PB) * 8;  // [tr][block parity]
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NBAND; ++s) {
+            mbar_init(full_s + s * 8, NLW * 32);
+            mbar_init(empty_s + s * 8, nvalid * ((DO_V && DO_L) ? 2 : 1));
+        }
+        for (int s = 0; s < NCW * 2 * (BX / PB); ++s) mbar_init(pubfull_s + s * 8, PB * ((DO_V && DO_L) ? 2 : 1));  // the batch's lanes arrive
+        for (int s = 0; s < NCW * 2; ++s) mbar_init(pubempty_s + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (nvalid == 0) return;
+
+    if (warp >= NCW && warp < NCW + NLW) {
+        // ---------------- loader warps: keep the ring of row bands filled ----------------------------
+        // band of row block j: rows y = 32j .. 32j+31, columns x = 32(j-ND) .. 32j+31, this solver's NQ tracks;
+        // chunk (e, cc) -> band + (e*BANDCOLS + cc)*16.  Chunks above the diagonal, left of column 0 or below
+        // row T-1 are never read and not fetched.
+        const int lt = threadIdx.x - NCW * 32;
+        const int nbytes = nvalid * 4;
+        for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
+            const int slot = it % NBAND;
+            if (it >= NBAND) mbar_wait(empty_s + slot * 8, ((it / NBAND) - 1) & 1, p.status);
+            const int y0 = j * BX, xlo = (j - ND) * BX;
+            const unsigned dst0 = band_s + (unsigned)(slot * kBandBytes);
+            for (int i = lt; i < BX * BANDCOLS; i += NLW * 32) {
+                const int e = i / BANDCOLS, cc = i - e * BANDCOLS;
+                const int y = y0 + e, x = xlo + cc;
+                if (x < 0 || x > y || y >= T) continue;
+                const float *src = p.Sbase + (long long)x * p.sx + (long long)y * p.sy + n0;
+                const unsigned dst = dst0 + (unsigned)i * 16u;
+                if (ALIGN == 16) {
+                    cp_async16_s(dst, src, nbytes);
+                } else if (ALIGN == 8) {
+                    cp_async8_s(dst, src, nvalid > 0 ? 8 : 0);
+                    if (nvalid > 2) cp_async8_s(dst + 8, src + 2, 8);
+                } else {
+                    for (int q = 0; q < nvalid; ++q) cp_async4_s(dst + q * 4, src + q, 4);
+                }
+            }
+            mbar_arrive_cp_async(full_s + slot * 8);
+        }
+        cp_async_wait_all();
+        return;
+    }
+    if (warp >= NCW + NLW && warp < NCW + NLW + NCW) {
+        // ---------------- publisher warps: one per track; results go shared memory -> mailbox and tables -----------
+        // (a global store issued by a chain warp costs it ~200 cycles per batch: profiles/r01_sweep_experiments.txt)
+        const int tr = warp - (NCW + NLW);
+        if (tr >= nvalid) return;
+        const int n = n0 + tr;
+        unsigned long long *mV = p.mbox + n, *mL = p.mbox + (size_t)T * p.Npad + n;
+        const int bmax_top = (T - (nb - 1) * BX - 1) / PB;  // last batch index of the ragged top block
+        for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
+            const int x0 = j * BX;
+            const int ncols = min(BX, T - x0);
+            for (int e8 = (ncols - 1) / PB; e8 >= 0; --e8) {
+                // batches the ragged top block skips never arrive: their barriers are one phase behind
+                const unsigned npast = (unsigned)(it >> 1) - (((it & 1) == 0 && it > 0 && e8 > bmax_top) ? 1u : 0u);
+                mbar_wait(pubfull_s + (unsigned)(((tr * 2 + (it & 1)) * (BX / PB) + e8) * 8), npast & 1, p.status);
+                const int c = e8 * PB + lane, x = x0 + c;
+                if (lane < PB && x < T) {
+                    const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
+                    const unsigned src = pub_s + (unsigned)((((tr * 2 + (it & 1)) * BX + c) * 2) * 8);
+                    if (DO_V) {
+                        const unsigned long long w = lds64(src);
+                        const float qfin = __uint_as_float((unsigned)w);
+                        publish(mV + (size_t)x * p.Npad, qfin, epoch);
+                        p.code[(size_t)n * T + pos] = (unsigned)(w >> 32);
+                        if (p.outv) p.outv[(size_t)pos * N + n] = qfin;
+                    }
+                    if (DO_L) {
+                        const unsigned long long w = lds64(src + 8);
+                        const float v2 = __uint_as_float((unsigned)w) + lg2f(__uint_as_float((unsigned)(w >> 32)));
+                        publish(mL + (size_t)x * p.Npad, v2, epoch);
+                        if (p.outl) p.outl[(size_t)pos * N + n] = v2 * kLn2;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pubempty_s + (tr * 2 + (it & 1)) * 8);
+        }
+        return;
+    }
+    // ---------------- chain warps ------------------------------------------------------------------------
+    ChainCtx cx;
+    cx.full_s = full_s;
+    cx.empty_s = empty_s;
+    cx.pub_s = pub_s;
+    cx.pubfull_s = pubfull_s;
+    cx.pubempty_s = pubempty_s;
+    cx.g = g;
+    cx.qd = qd;
+    cx.n0 = n0;
+    if (DO_V && DO_L) {  // split: Viterbi chains on warps 0..NCW-1, log-sum chains on the last NCW warps
+        if (warp < NCW) {
+            cx.tr = warp;
+            if (cx.tr < nvalid) chain_warp<DIR, true, false>(p, smem_raw, cx);
+        } else if (warp >= NW - NCW) {
+            cx.tr = warp - (NW - NCW);
+            if (cx.tr < nvalid) chain_warp<DIR, false, true>(p, smem_raw, cx);
+        }
+    } else if (warp < NCW) {
+        cx.tr = warp;
+        if (cx.tr < nvalid) chain_warp<DIR, DO_V, DO_L>(p, smem_raw, cx);
     }
 }
 
