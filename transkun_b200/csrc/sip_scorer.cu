@@ -7,13 +7,15 @@
 // (e >= b is all the semi-CRF ever reads; the reference computes the full square, multiplies it by the
 // length matrix, adds diag_embed and permutes -- four more passes over T*T*N).
 //
-// The output layout decides the tiling: a coalesced store needs the 8 tracks of one 32-byte sector
-// together, so one CTA computes a (128 ends x 64 begins) tile for a GROUP OF 8 TRACKS: eight 128x64
-// fp32 accumulators = all 512 TMEM columns.  Per (track, 32-wide K chunk) the operands (Q: 128 rows,
-// K: 64 rows, 128 B each) are staged with cp.async into 128B-swizzled K-major shared memory, and one
-// thread issues four tcgen05.mma.kind::tf32 (M128 N64 K8).  The epilogue reads TMEM with tcgen05.ld,
-// applies 1/sqrt(D) (a power of two for D=256, exact), the length factor, the diagonal and the triangle
-// mask, and stores full 32-byte sectors [e][b][8 tracks].
+// One CTA computes a (128 ends x 64 begins) tile for FOUR TRACKS (16 bytes of the track-innermost layout): four
+// 128x64 fp32 accumulators = 256 of the 512 TMEM columns, so two CTAs share an SM and one CTA's epilogue overlaps
+// the other's main loop.  The CTAs of the 22 track quads of a tile are dispatched together (quad = fastest block
+// index), so L2 sees both halves of every 32-byte sector before it evicts them.  Warp-specialised: warps 0-5
+// stage the operands per (track, 32-wide K chunk) (Q: 128 rows, K: 64 rows, 128 B each) with cp.async into
+// 128B-swizzled K-major shared memory (4 stages, full/empty mbarriers, no CTA barrier in the main loop), one
+// thread of warp 6 issues four tcgen05.mma.kind::tf32 (M128 N64 K8) per step and tcgen05.commit releases the
+// stage; all 8 warps run the epilogue: tcgen05.ld from TMEM, 1/sqrt(D) (a power of two for D=256, exact), the
+// length factor, the diagonal and the triangle mask, 16-byte stores [e][b][4 tracks].
 //
 // Precision: TF32 operands (the reference's own --allow_tf32 regime, train.py:41-43), fp32 accumulate.
 #include "common.cuh"
@@ -22,18 +24,24 @@ namespace tkb {
 
 constexpr int SC_TE = 128;      // ends per tile (= UMMA M)
 constexpr int SC_TB = 64;       // begins per tile (= UMMA N)
-constexpr int SC_NG = 8;        // tracks per CTA
+constexpr int SC_NG = 4;        // tracks per CTA: 4 x 64 fp32 accumulator columns = half of TMEM, two CTAs per SM
 constexpr int SC_KC = 32;       // tf32 elements per 128-byte swizzled row
 constexpr int SC_UMMA_K = 8;    // tf32 elements per tcgen05.mma
 constexpr int SC_THREADS = 256;
-constexpr int SC_STAGES = 5;
+constexpr int SC_PRODUCERS = 192;  // warps 0-5 stage the operands, warp 6 issues the MMAs, all 8 warps run the epilogue
+constexpr int SC_STAGES = 4;
+constexpr int SC_LOOKAHEAD = 2;    // cp.async groups a producer thread keeps in flight
 constexpr int SC_A_BYTES = SC_TE * 128;
 constexpr int SC_B_BYTES = SC_TB * 128;
 constexpr int SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;
 constexpr size_t kScorerSmem = (size_t)SC_STAGES * SC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert((SC_TE + SC_TB) * 8 % SC_PRODUCERS == 0, "pieces per producer thread");
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive1(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
@@ -91,21 +99,25 @@ struct ScorerParams {
 };
 
 // tile index -> (eb, bb): lower-triangular enumeration; row eb has nb_row(eb) = min(ceil(T/64), 2*eb + 2) tiles
-__global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerParams p) {
+__global__ void __launch_bounds__(SC_THREADS, 2) sip_scorer_kernel(const ScorerParams p) {
     extern __shared__ unsigned char smem_raw_sc[];
     const unsigned smem_base = (smem_u32(smem_raw_sc) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-B alignment
-    const unsigned bars = smem_base + SC_STAGES * SC_STAGE_BYTES;         // [SC_STAGES] mma_done, [1] acc_done
+    const unsigned bars = smem_base + SC_STAGES * SC_STAGE_BYTES;  // full[SC_STAGES], empty[SC_STAGES], acc_done
+    const unsigned full_b = bars, empty_b = bars + 8 * SC_STAGES, acc_b = bars + 16 * SC_STAGES;
     __shared__ unsigned tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = p.T, D = p.D, NT = p.NT;
-    const int g = blockIdx.y;
+    // track quads are the fastest-varying block index: the CTAs that write the two 16-byte halves of a 32-byte
+    // sector (and all 22 quads of a tile) are dispatched together, so L2 sees whole sectors before it evicts them
+    const int ngq = (NT + SC_NG - 1) / SC_NG;
+    const int g = (int)blockIdx.x % ngq;
     const int n0 = g * SC_NG;
     // decode (eb, bb) from blockIdx.x
     const int nbb = (T + SC_TB - 1) / SC_TB;
     int eb = 0, bb = 0;
     {
-        int rem = blockIdx.x;
+        int rem = (int)blockIdx.x / ngq;
         for (;;) {
             const int row = min(nbb, 2 * eb + 2);
             if (rem < row) {
@@ -123,12 +135,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"(512)
+                     "r"(SC_NG * SC_TB)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s <= SC_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+        for (int s = 0; s < SC_STAGES; ++s) {
+            mbar_init(full_b + 8 * s, SC_PRODUCERS);
+            mbar_init(empty_b + 8 * s, 1);
+        }
+        mbar_init(acc_b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -136,15 +152,15 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = tmem_base_s;
 
-    // operand loader: step s = (track t, K chunk kc); 1536 16-byte pieces per step, 6 per thread
+    // operand loader: step s = (track t, K chunk kc); 1536 16-byte pieces per step, 8 per producer thread
     auto load_step = [&](int s) {
         const int t = s / nchunks, kc = s - t * nchunks;
         const unsigned stage = smem_base + (unsigned)(s % SC_STAGES) * SC_STAGE_BYTES;
         const float *qn = p.q + ((size_t)(n0 + t) * T) * D + kc * SC_KC;
         const float *kn = p.k + ((size_t)(n0 + t) * T) * D + kc * SC_KC;
 #pragma unroll
-        for (int i = 0; i < (SC_TE + SC_TB) * 8 / SC_THREADS; ++i) {
-            const int piece = tid + i * SC_THREADS;
+        for (int i = 0; i < (SC_TE + SC_TB) * 8 / SC_PRODUCERS; ++i) {
+            const int piece = tid + i * SC_PRODUCERS;
             const int row = piece >> 3, ch = piece & 7;
             const bool isA = row < SC_TE;
             const int r = isA ? row : row - SC_TE;
@@ -156,24 +172,31 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
     };
 
     const unsigned idesc = umma_idesc_tf32(SC_TE, SC_TB);
+    if (tid < SC_PRODUCERS) {
+        // ---- producers: fill stage s % SC_STAGES once the MMAs that read it have completed (empty), hand it over
+        // (full) when this thread's pieces have landed; SC_LOOKAHEAD groups in flight per thread, no CTA barrier
+        auto hand_over = [&](int s) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async writes -> visible to the tensor core
+            mbar_arrive1(full_b + 8 * (s % SC_STAGES));
+        };
 #pragma unroll 1
-    for (int s = 0; s < SC_STAGES - 1; ++s) {
-        if (s < nsteps) load_step(s);
-        cp_async_commit();
-    }
-#pragma unroll 1
-    for (int s = 0; s < nsteps; ++s) {
-        // the stage about to be refilled was read by the MMAs of step s-1: wait for their completion
-        const int sl = s + SC_STAGES - 1;
-        if (sl < nsteps) {
-            if (s >= 1) mbar_wait(bars + 8 * ((s - 1) % SC_STAGES), (unsigned)(((s - 1) / SC_STAGES) & 1));
-            load_step(sl);
+        for (int s = 0; s < nsteps; ++s) {
+            if (s >= SC_STAGES) mbar_wait(empty_b + 8 * (s % SC_STAGES), (unsigned)(((s / SC_STAGES) - 1) & 1));
+            load_step(s);
+            cp_async_commit();
+            if (s >= SC_LOOKAHEAD) {
+                cp_async_wait<SC_LOOKAHEAD>();
+                hand_over(s - SC_LOOKAHEAD);
+            }
         }
-        cp_async_commit();
-        cp_async_wait<SC_STAGES - 1>();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
+        cp_async_wait_all();
+#pragma unroll 1
+        for (int s = max(nsteps - SC_LOOKAHEAD, 0); s < nsteps; ++s) hand_over(s);
+    } else if (tid == SC_PRODUCERS) {
+        // ---- MMA issuer: one thread; tcgen05.commit releases the stage when its four MMAs are done
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+            mbar_wait(full_b + 8 * (s % SC_STAGES), (unsigned)((s / SC_STAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int t = s / nchunks, kc = s - t * nchunks;
             const unsigned stage = smem_base + (unsigned)(s % SC_STAGES) * SC_STAGE_BYTES;
@@ -181,12 +204,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
 #pragma unroll
             for (int kk = 0; kk < SC_KC / SC_UMMA_K; ++kk)  // +32 bytes along K inside the swizzle atom = +2 in the address field
                 umma_tf32(tmem_base + t * SC_TB, da + 2 * kk, db + 2 * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bars + 8 * (s % SC_STAGES));
-            if (s == nsteps - 1) umma_commit(bars + 8 * SC_STAGES);
+            umma_commit(empty_b + 8 * (s % SC_STAGES));
         }
+        umma_commit(acc_b);
     }
+    __syncwarp();
     // all accumulators complete
-    mbar_wait(bars + 8 * SC_STAGES, 0);
+    mbar_wait(acc_b, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // epilogue: warp w reads TMEM lanes 32*(w%4).., warps 0-3 take begins 0..31 of the tile, warps 4-7 begins 32..63
@@ -221,7 +245,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
                     float *o = p.out + ((size_t)e * T + b) * NT + n0;
                     if (vec_ok && ntrk == SC_NG) {
                         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     } else {
 #pragma unroll
                         for (int t = 0; t < SC_NG; ++t)
@@ -233,7 +256,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sip_scorer_kernel(const ScorerP
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(SC_NG * SC_TB) : "memory");
 }
 
 }  // namespace tkb
@@ -266,7 +290,7 @@ extern "C" int tkb_sip_score(const float *q, const float *k, const float *diag, 
     long long tiles = 0;
     for (int eb = 0; eb < neb; ++eb) tiles += (2 * eb + 2 < nbb) ? 2 * eb + 2 : nbb;
     p.tiles_b_total = (int)tiles;
-    dim3 grid((unsigned)tiles, (unsigned)((n_tracks + SC_NG - 1) / SC_NG));
+    dim3 grid((unsigned)(tiles * ((n_tracks + SC_NG - 1) / SC_NG)));
     sip_scorer_kernel<<<grid, SC_THREADS, kScorerSmem, (cudaStream_t)stream_>>>(p);
     TKB_CUDA(cudaGetLastError());
     return 0;
