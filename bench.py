@@ -256,12 +256,15 @@ def run_ours(args):
     fence()
     e2e_steps = max(1, args.e2e_steps)
     d2h_bytes = 0
+    with torch.no_grad():  # one untimed pass: first-use allocations of the e2e path
+        NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev).decodeWithLogZ()
+    torch.cuda.synchronize(dev)
     tw0 = time.perf_counter()
     for _ in range(e2e_steps):
-        s_dev = score_pin.to(dev, non_blocking=True)
-        z_dev = noise_pin.to(dev, non_blocking=True)
         with torch.no_grad():
-            dec, logz = NeuralSemiCRFInterval(s_dev, z_dev).decodeWithLogZ()
+            # public API from HOST tensors: uploads the part of the score tensor the semi-CRF reads (end >= begin)
+            crf = NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev)
+            dec, logz = crf.decodeWithLogZ()
             logz_h = logz.cpu()
         maxc = max((len(d) for d in dec), default=0)
         d2h_bytes = n_local * 4 + n_local * maxc * 8 + logz_h.numel() * 4
@@ -271,7 +274,7 @@ def run_ours(args):
         tmax = torch.tensor([e2e_sec], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_sec = float(tmax.item())
-    h2d_bytes = score_pin.numel() * 4 + noise_pin.numel() * 4
+    h2d_bytes = NeuralSemiCRFInterval.lowerTriangleUploadBytes(T, n_local) + noise_pin.numel() * 4
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -289,7 +292,8 @@ def run_ours(args):
                        "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks"},
             "e2e": {"value": cells_per_step / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "api": "NeuralSemiCRFInterval(score, noise).decodeWithLogZ() from pinned host tensors"},
+                    "api": "NeuralSemiCRFInterval.fromHost(score, noise, device).decodeWithLogZ() from pinned host tensors "
+                           "(uploads the lower-triangle staircase of score, the part the semi-CRF reads)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "tkb::sweep_kernel<BACKWARD, A16, VITERBI|LOGSUM>",

@@ -60,6 +60,17 @@ int tkb_device_check(void);
 size_t tkb_sweep_workspace_bytes(int T, int N);
 
 /*
+ * Host -> device upload of the part of score[T][T][N] the semi-CRF reads (end >= begin), for callers whose
+ * score tensor lives in (pinned) host memory: the reference moves the dense tensor with `.cuda()` /
+ * `.to(device)` before constructing the object (crfMinimalExample.py:13-14, README usage); this moves the
+ * staircase of row chunks instead, about half the bytes.  host_score and dev_score are [T][T][N] fp32,
+ * contiguous; cells above the staircase keep whatever dev_score held.  Asynchronous on `stream`.
+ */
+int tkb_upload_lower_triangle(const float *host_score, float *dev_score, int T, int N, int rows_per_chunk,
+                              void *stream);
+
+
+/*
  * The semi-Markov dynamic programme over the lower triangle of score.
  * Replaces the TorchScript loops of
  *   CRF/NeuralSemiCRFInterval.py:31-51   viterbiBackward   (BACKWARD | VITERBI)

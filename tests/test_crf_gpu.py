@@ -206,3 +206,25 @@ def test_strip_design_parity_ladder():
                           "33,8,randn", "65,9,ties", "100,4,model", "256,90,ties", "691,90,model", "300,180,randn",
                           "1024,88,randn"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert "ALL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_from_host_uploads_only_what_is_read():
+    """fromHost moves the lower-triangle staircase of a pinned host tensor; results equal the dense upload, even
+    when everything above the diagonal is NaN on the host (the semi-CRF never reads end < begin)."""
+    from golden_util import make_inputs
+    from transkun_b200.CRF import NeuralSemiCRFInterval
+    T, N = 200, 12
+    score, noise = make_inputs("randn", T, N, 3)
+    dense = NeuralSemiCRFInterval(torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda())
+    poisoned = score.copy()
+    iu = np.triu_indices(T, 1)
+    poisoned[iu[0], iu[1], :] = np.nan
+    host = NeuralSemiCRFInterval.fromHost(torch.from_numpy(poisoned).pin_memory(), torch.from_numpy(noise).pin_memory(), "cuda")
+    with torch.no_grad():
+        d0, z0 = dense.decodeWithLogZ()
+        d1, z1 = host.decodeWithLogZ()
+        assert d0 == d1
+        assert torch.equal(z0, z1)
+        assert torch.equal(dense.computeLogZ(noBackward=True), host.computeLogZ(noBackward=True))
+    assert NeuralSemiCRFInterval.lowerTriangleUploadBytes(T, N) < 0.7 * score.nbytes

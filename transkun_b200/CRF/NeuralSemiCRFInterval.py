@@ -166,11 +166,12 @@ def _csr(intervals: Intervals, N: int, T: int, dev):
 def _pairs_to_lists(pairs: torch.Tensor, counts: torch.Tensor) -> Intervals:
     counts_h = counts.cpu()  # synchronises (the reference synchronises at ptr.cpu(), :56)
     maxc = int(counts_h.max()) if counts_h.numel() else 0
-    pairs_h = pairs[:, :maxc].cpu().numpy() if maxc > 0 else np.zeros((pairs.shape[0], 0, 2), dtype=np.int32)
-    out: Intervals = []
-    for n, c in enumerate(counts_h.tolist()):
-        out.append(list(map(tuple, pairs_h[n, :c].tolist())))
-    return out
+    if maxc == 0:
+        return [[] for _ in range(pairs.shape[0])]
+    pairs_h = pairs[:, :maxc].cpu().numpy()
+    # two flat int lists per track zipped into tuples: ~5x faster than tuple() over a list of 2-lists
+    begins, ends = pairs_h[:, :, 0], pairs_h[:, :, 1]
+    return [list(zip(begins[n, :c].tolist(), ends[n, :c].tolist())) for n, c in enumerate(counts_h.tolist())]
 
 
 # ---------------------------------------------------------------------------
@@ -311,6 +312,32 @@ class NeuralSemiCRFInterval:
         """
         self.score = score
         self.noiseScore = noiseScore
+
+    @classmethod
+    def fromHost(cls, score: torch.Tensor, noiseScore: torch.Tensor, device, rows_per_chunk: int = 64):
+        """Build the object from HOST tensors (the reference's users call `.cuda()` on both first,
+        crfMinimalExample.py:13-14).  Only the part of `score` the semi-CRF reads (end >= begin) is uploaded -- a
+        staircase of strided 2-D copies, about half the bytes of the dense tensor; the rest of the device tensor is
+        zero.  Asynchronous on the current stream when the host tensors are pinned."""
+        device = torch.device(device)
+        assert score.dim() == 3 and score.shape[0] == score.shape[1], "score must be [T, T, nBatch]"
+        if score.is_cuda or noiseScore.is_cuda:
+            raise RuntimeError("fromHost expects host tensors")
+        T, N = score.shape[0], score.shape[2]
+        s = score.detach().to(torch.float32).contiguous()
+        dev_score = torch.zeros((T, T, N), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rc = _lib.load().tkb_upload_lower_triangle(s.data_ptr(), dev_score.data_ptr(), T, N, rows_per_chunk,
+                                                       _stream(device))
+        _lib.check(rc, "tkb_upload_lower_triangle")
+        obj = cls(dev_score, noiseScore.detach().to(torch.float32).to(device, non_blocking=True))
+        obj._host_keepalive = s  # the copies are asynchronous
+        return obj
+
+    @staticmethod
+    def lowerTriangleUploadBytes(T: int, N: int, rows_per_chunk: int = 64) -> int:
+        return sum((min(e0 + rows_per_chunk, T) - e0) * min(e0 + rows_per_chunk, T) * N * 4
+                   for e0 in range(0, T, rows_per_chunk))
 
     # -- packed device-side results (what a fused caller should use) -----------------------
     def decode_packed(self, forcedStartPos=None, forward: bool = False, with_logz: bool = False):

@@ -21,6 +21,7 @@ EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
     "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
     "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_logmel_workspace_bytes", "tkb_logmel",
+    "tkb_upload_lower_triangle",
 )
 
 
@@ -77,6 +78,8 @@ def load() -> ctypes.CDLL:
     L.tkb_logmel_workspace_bytes.argtypes = [i, i, i, i, i]
     L.tkb_logmel.restype = i
     L.tkb_logmel.argtypes = [vp, i64, i64, i64, i, i, i, i, vp, i, vp, vp, vp, i, i, f, vp, vp, vp]
+    L.tkb_upload_lower_triangle.restype = i
+    L.tkb_upload_lower_triangle.argtypes = [vp, vp, i, i, i, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

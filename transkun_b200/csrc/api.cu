@@ -44,3 +44,22 @@ extern "C" int tkb_device_check(void) {
     }
     return 0;
 }
+
+// Host -> device copy of the part of score[T][T][N] the semi-CRF reads: rows are taken in chunks of `rows_per_chunk`,
+// chunk [e0, e1) is one strided 2-D copy of its first e1 cells per row (a superset of b <= e).  Halves the bytes
+// of the dense upload; what lies above the copied staircase is left untouched in the destination.
+extern "C" int tkb_upload_lower_triangle(const float *host_score, float *dev_score, int T, int N, int rows_per_chunk,
+                                         void *stream_) {
+    if (!host_score || !dev_score || T < 1 || N < 1 || rows_per_chunk < 1) {
+        tkb::set_error("tkb_upload_lower_triangle: invalid argument (T=%d N=%d rows_per_chunk=%d)", T, N, rows_per_chunk);
+        return TKB_EINVAL;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t pitch = (size_t)T * N * sizeof(float);
+    for (int e0 = 0; e0 < T; e0 += rows_per_chunk) {
+        const int e1 = e0 + rows_per_chunk < T ? e0 + rows_per_chunk : T;
+        TKB_CUDA(cudaMemcpy2DAsync(dev_score + (size_t)e0 * T * N, pitch, host_score + (size_t)e0 * T * N, pitch,
+                                   (size_t)e1 * N * sizeof(float), (size_t)(e1 - e0), cudaMemcpyHostToDevice, stream));
+    }
+    return 0;
+}
