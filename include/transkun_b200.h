@@ -95,6 +95,17 @@ int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int 
                       float *out_lse, void *stream);
 
 /*
+ * Same, for a score tensor whose track axis is padded: cell (end, begin) starts at
+ * score + (end * T + begin) * pitch and holds N <= pitch tracks.  A pitch that is a multiple of 4 (with a
+ * 16-byte aligned base) keeps the 16-byte copy path for track counts like the model's N = 90
+ * (ModelTransformer.py:97: 88 keys + 2 pedals), which a dense [T,T,90] tensor cannot offer.
+ * tkb_semicrf_sweep(...) == tkb_semicrf_sweep_pitched(score, N, ...).
+ */
+int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, const float *noise, int T, int N, int direction,
+                              int flags, void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit,
+                              float *out_lse, void *stream);
+
+/*
  * Reads the status word of a sweep workspace (synchronises `stream`).
  * *status_host (HOST pointer) = 0 if every sweep that used the workspace ran to
  * completion, non-zero if an inter-CTA wait timed out (results invalid).
@@ -162,6 +173,11 @@ int tkb_semicrf_evalpath_grad(int T, int N, const int32_t *pairs, const int64_t 
  */
 int tkb_sip_score(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
                   float *out_score, void *stream);
+
+/* Same, writing cell (end, begin) at out_score + (end * T + begin) * pitch (pitch >= n_tracks): a pitch that is a
+ * multiple of 4 gives the semi-CRF sweep its 16-byte copy path for n_tracks = 90 (tkb_semicrf_sweep_pitched). */
+int tkb_sip_score_pitched(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
+                          float *out_score, int64_t pitch, void *stream);
 
 /*
  * STFT / log-mel frontend.  Replaces Util.py:104-113 (Spectrum.forward) and :156-167

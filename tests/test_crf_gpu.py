@@ -228,3 +228,52 @@ def test_from_host_uploads_only_what_is_read():
         assert torch.equal(z0, z1)
         assert torch.equal(dense.computeLogZ(noBackward=True), host.computeLogZ(noBackward=True))
     assert NeuralSemiCRFInterval.lowerTriangleUploadBytes(T, N) < 0.7 * score.nbytes
+
+
+@pytest.mark.gpu
+def test_packed_intervals_equal_lists():
+    """evalPath / logProb accept the intervals pre-packed (pairs + CSR offsets): same values and gradients."""
+    from golden_util import make_inputs
+    from transkun_b200.CRF import NeuralSemiCRFInterval, pack_intervals
+    T, N = 120, 9
+    score, noise = make_inputs("randn", T, N, 5)
+    out = []
+    for packed in (False, True):
+        s = torch.from_numpy(score).cuda().requires_grad_()
+        z = torch.from_numpy(noise).cuda().requires_grad_()
+        crf = NeuralSemiCRFInterval(s, z)
+        with torch.no_grad():
+            iv = crf.decode()
+        arg = pack_intervals(iv, T) if packed else iv
+        lp = crf.logProb(arg)
+        lp.sum().backward()
+        out.append((lp.detach(), s.grad.clone(), z.grad.clone(), crf.evalPath(arg).detach()))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(97, 90), (300, 90), (65, 9), (691, 90)])
+def test_padded_track_axis_equals_dense(T, N):
+    """A score tensor whose track axis is padded to a multiple of 4 (what the scorer emits for the model's 90
+    symbols; strides (T*P, P, 1)) goes through tkb_semicrf_sweep_pitched without a copy and decodes exactly like
+    the dense tensor; large dense tensors with N % 4 != 0 are re-laid out once (same results)."""
+    from golden_util import make_inputs
+    from oracle.semicrf_oracle import SemiCRFOracle
+    from transkun_b200.CRF import NeuralSemiCRFInterval
+    score, noise = make_inputs("randn", T, N, 21)
+    P = (N + 3) // 4 * 4
+    buf = torch.full((T, T, P), float("nan"), device="cuda")
+    buf[:, :, :N] = torch.from_numpy(score).cuda()
+    padded = buf[:, :, :N]
+    assert not padded.is_contiguous()
+    z = torch.from_numpy(noise).cuda()
+    o = SemiCRFOracle(score, noise)
+    with torch.no_grad():
+        for s in (padded, torch.from_numpy(score).cuda()):
+            crf = NeuralSemiCRFInterval(s, z)
+            dec, logz = crf.decodeWithLogZ()
+            assert dec == o.decode()
+            assert crf.decode(forward=True) == o.decode(forward=True)
+            np.testing.assert_allclose(logz.cpu().numpy(), o.computeLogZ(), rtol=RTOL)
+            np.testing.assert_allclose(crf.computeLogZ(noBackward=True).cpu().numpy(), o.computeLogZ(), rtol=RTOL)

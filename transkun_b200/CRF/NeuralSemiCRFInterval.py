@@ -14,6 +14,7 @@ no CPU path: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
+import itertools
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -86,20 +87,49 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def _pitched(t: torch.Tensor) -> bool:
+    """[T, T, N] with the track axis contiguous and padded: strides (T * P, P, 1), P >= N."""
+    return t.dim() == 3 and t.stride(2) == 1 and t.stride(1) >= t.shape[2] and t.stride(0) == t.shape[0] * t.stride(1)
+
+
+_PAD_MIN_ELEMS = 1 << 22  # below this a sweep is launch-bound and the padding pass does not pay
+
+
+def _prep_score_for_sweep(t: torch.Tensor) -> torch.Tensor:
+    """The score tensor as the sweep wants it: fp32, track axis contiguous.  A track count that is not a multiple
+    of 4 (the model's 90) only allows 8- or 4-byte copies from a dense tensor; a tensor that already comes padded
+    (what our scorer emits) is used as it is, a dense one is re-laid out once with the track axis padded to a
+    multiple of 4 when it is large enough for the extra pass to pay."""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    N = t.shape[2]
+    if _pitched(t) and (t.stride(1) % 4 == 0 or t.is_contiguous()):
+        if t.is_contiguous() and N % 4 != 0 and t.numel() >= _PAD_MIN_ELEMS:
+            buf = torch.zeros((t.shape[0], t.shape[1], (N + 3) // 4 * 4), dtype=torch.float32, device=t.device)
+            buf[:, :, :N].copy_(t)
+            return buf[:, :, :N]
+        return t
+    return t.contiguous()
+
+
 def sweep(score: torch.Tensor, noise: torch.Tensor, direction: int, flags: int, want_vit: bool = False,
           slot: int = 0):
-    """One pass of the persistent DP kernel.  Returns (code[N,T] int32 | None, vit[T,N] | None, lse[T,N] | None)."""
+    """One pass of the persistent DP kernel.  Returns (code[N,T] int32 | None, vit[T,N] | None, lse[T,N] | None).
+    `score` may have a padded track axis (strides (T*P, P, 1))."""
     T, N = score.shape[0], score.shape[2]
     dev = score.device
     L = _lib.load()
+    assert _pitched(score), "score must be [T, T, N] with a contiguous (possibly padded) track axis"
     ws = _workspace(T, N, dev, slot)
     code = torch.empty((N, T), dtype=torch.int32, device=dev) if flags & SWEEP_VITERBI else None
     vit = torch.empty((T, N), dtype=torch.float32, device=dev) if (flags & SWEEP_VITERBI and want_vit) else None
     lse = torch.empty((T, N), dtype=torch.float32, device=dev) if flags & SWEEP_LOGSUM else None
     with torch.cuda.device(dev):
-        rc = L.tkb_semicrf_sweep(_ptr(score), _ptr(noise) if T > 1 else None, T, N, direction, flags,
-                                 _ptr(ws.buf), ws.next_epoch(), _ptr(code), _ptr(vit), _ptr(lse), _stream(dev))
-    _lib.check(rc, "tkb_semicrf_sweep")
+        rc = L.tkb_semicrf_sweep_pitched(_ptr(score), score.stride(1), _ptr(noise) if T > 1 else None, T, N, direction,
+                                         flags, _ptr(ws.buf), ws.next_epoch(), _ptr(code), _ptr(vit), _ptr(lse),
+                                         _stream(dev))
+    _lib.check(rc, "tkb_semicrf_sweep_pitched")
     return code, vit, lse, ws
 
 
@@ -148,19 +178,42 @@ def _forced_tensor(forcedStartPos: Optional[Sequence[int]], N: int, T: int, dev)
     return f.contiguous()
 
 
-def _csr(intervals: Intervals, N: int, T: int, dev):
-    if len(intervals) != N:
-        raise ValueError(f"intervals must have one list per track ({N}), got {len(intervals)}")
+class PackedIntervals:
+    """Interval lists as two arrays: pairs [M, 2] int32 (begin, end) and offsets [N + 1] int64 (CSR).  Build it once
+    (e.g. in the data loader) with `pack_intervals` and pass it wherever the reference takes the list of lists
+    (`evalPath`, `logProb`): the per-call flattening of ~10^5 Python tuples is the largest cost of a training step."""
+
+    def __init__(self, pairs: torch.Tensor, offsets: torch.Tensor):
+        assert pairs.dim() == 2 and pairs.shape[1] == 2 and offsets.dim() == 1
+        self.pairs = pairs.to(torch.int32).contiguous()
+        self.offsets = offsets.to(torch.int64).contiguous()
+
+
+def pack_intervals(intervals: Intervals, T: Optional[int] = None) -> PackedIntervals:
+    N = len(intervals)
     lens = np.fromiter((len(c) for c in intervals), dtype=np.int64, count=N)
     offsets = np.zeros(N + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
-    flat = np.asarray([p for cur in intervals for p in cur], dtype=np.int32).reshape(-1, 2)
-    if flat.size and (flat.min() < 0 or flat.max() >= T):
+    # one C-level pass over all endpoints (a list comprehension of tuples + np.asarray is 3x slower)
+    flat = np.fromiter(itertools.chain.from_iterable(itertools.chain.from_iterable(intervals)), dtype=np.int32,
+                       count=2 * int(offsets[-1])).reshape(-1, 2)
+    if T is not None and flat.size and (flat.min() < 0 or flat.max() >= T):
         raise IndexError("interval endpoints must lie in [0, T)")
-    pairs = torch.from_numpy(np.ascontiguousarray(flat)).to(dev, non_blocking=True)
-    if pairs.numel() == 0:
-        pairs = torch.zeros((1, 2), dtype=torch.int32, device=dev)
-    return pairs, torch.from_numpy(offsets).to(dev, non_blocking=True)
+    return PackedIntervals(torch.from_numpy(np.ascontiguousarray(flat)), torch.from_numpy(offsets))
+
+
+def _csr(intervals, N: int, T: int, dev):
+    if isinstance(intervals, PackedIntervals):
+        if intervals.offsets.numel() != N + 1:
+            raise ValueError(f"intervals must have one list per track ({N}), got {intervals.offsets.numel() - 1}")
+        pairs = intervals.pairs.to(dev, non_blocking=True)
+        if pairs.numel() == 0:
+            pairs = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        return pairs, intervals.offsets.to(dev, non_blocking=True)
+    if len(intervals) != N:
+        raise ValueError(f"intervals must have one list per track ({N}), got {len(intervals)}")
+    packed = pack_intervals(intervals, T)
+    return _csr(packed, N, T, dev)
 
 
 def _pairs_to_lists(pairs: torch.Tensor, counts: torch.Tensor) -> Intervals:
@@ -345,7 +398,7 @@ class NeuralSemiCRFInterval:
         score.device, nothing synchronised.  with_logz=True also evaluates the log-partition in the SAME
         pass over the score tensor (BACKWARD direction only, where both tables walk the triangle alike)."""
         T, N = _check_inputs(self.score, self.noiseScore)
-        s, z = _prep(self.score), _prep(self.noiseScore)
+        s, z = _prep_score_for_sweep(self.score), _prep(self.noiseScore)
         direction = FORWARD if forward else BACKWARD
         flags = SWEEP_VITERBI | (SWEEP_LOGSUM if with_logz else 0)
         code, _, lse, ws = sweep(s, z, direction, flags)
@@ -391,7 +444,7 @@ class NeuralSemiCRFInterval:
             # noBackward=True differentiates the same value through autograd in the reference (:583);
             # the closed-form marginals are that gradient
             return _LogZFn.apply(self.score, self.noiseScore)
-        s, z = _prep(self.score), _prep(self.noiseScore)
+        s, z = _prep_score_for_sweep(self.score), _prep(self.noiseScore)
         _, _, alpha, _ = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
         return alpha[-1].clone()
 

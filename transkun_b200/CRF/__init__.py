@@ -1,2 +1,2 @@
 # mirrors reference transkun/CRF/__init__.py:1
-from .NeuralSemiCRFInterval import NeuralSemiCRFInterval  # noqa: F401
+from .NeuralSemiCRFInterval import NeuralSemiCRFInterval, PackedIntervals, pack_intervals  # noqa: F401

@@ -23,18 +23,25 @@ from . import _lib
 
 
 def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-    """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle defined)."""
+    """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle defined).
+
+    When NT is not a multiple of 4 (the model: 90 symbols) the result is a [T, T, NT] view of a buffer whose track
+    axis is padded to a multiple of 4 (strides (T*P, P, 1)): the semi-CRF sweep then keeps its 16-byte copy path
+    (tkb_semicrf_sweep_pitched) instead of the 8-byte one a dense [T, T, 90] tensor forces."""
     if not (q.is_cuda and k.is_cuda and diag.is_cuda):
         raise RuntimeError("transkun_b200 has no CPU path: scorer inputs must be CUDA tensors")
     NT, T, D = q.shape
     assert k.shape == (NT, T, D) and diag.shape == (NT, T)
     q, k, diag = q.float().contiguous(), k.float().contiguous(), diag.float().contiguous()
     if out is None:
-        out = torch.empty((T, T, NT), dtype=torch.float32, device=q.device)
+        P = (NT + 3) // 4 * 4
+        out = torch.zeros((T, T, P), dtype=torch.float32, device=q.device)[:, :, :NT] if P != NT else \
+            torch.empty((T, T, NT), dtype=torch.float32, device=q.device)
+    assert out.shape == (T, T, NT) and out.stride(2) == 1 and out.stride(0) == T * out.stride(1)
     with torch.cuda.device(q.device):
-        rc = _lib.load().tkb_sip_score(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, D, out.data_ptr(),
-                                       torch.cuda.current_stream(q.device).cuda_stream)
-    _lib.check(rc, "tkb_sip_score")
+        rc = _lib.load().tkb_sip_score_pitched(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, D, out.data_ptr(),
+                                               out.stride(1), torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(rc, "tkb_sip_score_pitched")
     return out
 
 

@@ -19,8 +19,9 @@ SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
 # every symbol include/transkun_b200.h declares
 EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
+    "tkb_semicrf_sweep_pitched",
     "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
-    "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_logmel_workspace_bytes", "tkb_logmel",
+    "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_sip_score_pitched", "tkb_logmel_workspace_bytes", "tkb_logmel",
     "tkb_upload_lower_triangle",
 )
 
@@ -59,6 +60,8 @@ def load() -> ctypes.CDLL:
     L.tkb_sweep_workspace_bytes.argtypes = [i, i]
     L.tkb_semicrf_sweep.restype = i
     L.tkb_semicrf_sweep.argtypes = [vp, vp, i, i, i, i, vp, u32, vp, vp, vp, vp]
+    L.tkb_semicrf_sweep_pitched.restype = i
+    L.tkb_semicrf_sweep_pitched.argtypes = [vp, ctypes.c_int64, vp, i, i, i, i, vp, u32, vp, vp, vp, vp]
     L.tkb_sweep_status.restype = i
     L.tkb_sweep_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int), vp]
     L.tkb_semicrf_backtrack.restype = i
@@ -71,6 +74,8 @@ def load() -> ctypes.CDLL:
     L.tkb_semicrf_evalpath.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp]
     L.tkb_semicrf_evalpath_grad.restype = i
     L.tkb_semicrf_evalpath_grad.argtypes = [i, i, vp, vp, vp, f, vp, vp, vp]
+    L.tkb_sip_score_pitched.restype = i
+    L.tkb_sip_score_pitched.argtypes = [vp, vp, vp, i, i, i, vp, ctypes.c_int64, vp]
     L.tkb_sip_score.restype = i
     L.tkb_sip_score.argtypes = [vp, vp, vp, i, i, i, vp, vp]
     i64 = ctypes.c_int64

@@ -15,8 +15,8 @@ int cuda_fail(cudaError_t e, const char *what);  // records the error, returns (
 // experimental strip design of the sweep (semicrf_sweep_strip.cu), selected with TKB_SWEEP=strip
 namespace strip {
 size_t workspace_bytes(int T, int N);
-int sweep(const float *score, const float *noise, int T, int N, int direction, int flags, void *workspace,
-          uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream);
+int sweep(const float *score, long long pitch, const float *noise, int T, int N, int direction, int flags,
+          void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream);
 void set_timeline(unsigned long long *buf);
 }  // namespace strip
 

@@ -52,7 +52,10 @@ constexpr int NW = 16;     // warps per CTA (helper: 16 row slices; solver: 4 ch
 constexpr int NT = NW * 32;
 constexpr int NCW = NQ;    // chain warps
 constexpr int NLW = 4;     // loader warps
-constexpr int SLOTS = 4;   // helper: per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
+#ifndef TKB_SLOTS
+#define TKB_SLOTS 4
+#endif
+constexpr int SLOTS = TKB_SLOTS;  // helper: per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
 constexpr int PB = 8;      // rows per publish batch
 #ifndef TKB_FARFETCH_BATCH
 #define TKB_FARFETCH_BATCH 3
@@ -280,7 +283,7 @@ __device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char 
             auto issue = [&]() {
                 const int live = ti < mypairs;
                 const int liveB = live && (2 * (warp + ti * NW) + 1 < R);
-                const unsigned so = (unsigned)(ti & (SLOTS - 1)) * 2048u;
+                const unsigned so = (unsigned)(ti % SLOTS) * 2048u;
                 if (A16) {
                     cp_async16_s(ring_s + so, sp0, live ? nbytes : 0);
                     cp_async16_s(ring_s + so + 512, sp0 + scol, live ? nbytes : 0);
@@ -325,7 +328,7 @@ __device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char 
                 cp_async_commit();
                 cp_async_wait<D>();
                 __syncwarp();
-                const unsigned so = (unsigned)(t & (SLOTS - 1));
+                const unsigned so = (unsigned)(t % SLOTS);
                 const bool hasB = 2 * (warp + t * NW) + 1 < R;
                 unsigned long long word = lds64(q_s + so * 256 + lane * 8);
                 const bool need = c_need && (c_row == 0 || hasB);
@@ -880,13 +883,21 @@ extern "C" size_t tkb_sweep_workspace_bytes(int T, int N) {
 extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
                                  void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit,
                                  float *out_lse, void *stream_) {
+    return tkb_semicrf_sweep_pitched(score, N, noise, T, N, direction, flags, workspace, epoch, out_code, out_vit, out_lse,
+                                     stream_);
+}
+
+extern "C" int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, const float *noise, int T, int N,
+                                         int direction, int flags, void *workspace, uint32_t epoch,
+                                         uint32_t *out_code, float *out_vit, float *out_lse, void *stream_) {
     if (use_strip())
-        return strip::sweep(score, noise, T, N, direction, flags, workspace, epoch, out_code, out_vit, out_lse, stream_);
+        return strip::sweep(score, pitch, noise, T, N, direction, flags, workspace, epoch, out_code, out_vit, out_lse,
+                            stream_);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!score || !workspace || T < 1 || N < 1 || (T > 1 && !noise) || epoch == 0 ||
         (direction != TKB_BACKWARD && direction != TKB_FORWARD) ||
         (flags & ~(TKB_SWEEP_VITERBI | TKB_SWEEP_LOGSUM)) || flags == 0 ||
-        ((flags & TKB_SWEEP_VITERBI) && !out_code) || (long long)T * T >= (1ll << 40)) {
+        ((flags & TKB_SWEEP_VITERBI) && !out_code) || (long long)T * T >= (1ll << 40) || pitch < N) {
         set_error("tkb_semicrf_sweep: invalid argument (T=%d N=%d dir=%d flags=%d epoch=%u)", T, N, direction,
                   flags, epoch);
         return TKB_EINVAL;
@@ -913,19 +924,20 @@ extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, 
     p.timeline = g_timeline;
     if (direction == TKB_BACKWARD) {
         p.Sbase = score;
-        p.sx = N;
-        p.sy = (long long)T * N;
+        p.sx = pitch;
+        p.sy = (long long)T * pitch;
         p.etabase = noise;
         p.se = N;
     } else {
-        p.Sbase = score + ((long long)(T - 1) * T + (T - 1)) * N;
-        p.sx = -(long long)T * N;
-        p.sy = -(long long)N;
+        p.Sbase = score + ((long long)(T - 1) * T + (T - 1)) * pitch;
+        p.sx = -(long long)T * pitch;
+        p.sy = -(long long)pitch;
         p.etabase = noise ? noise + (long long)(T - 2) * N : nullptr;  // skip weight of x is noise[T-2-x]
         p.se = -(long long)N;
     }
     const uintptr_t addr = reinterpret_cast<uintptr_t>(score);
-    const int align = (N % 4 == 0 && (addr & 15) == 0) ? 16 : ((N % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
+    // the track pitch, not N, decides the copy width: a padded score tensor (pitch % 4 == 0) takes the 16-byte path
+    const int align = (pitch % 4 == 0 && (addr & 15) == 0) ? 16 : ((pitch % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
     const int nb = (T + BX - 1) / BX;
     const int hmax = nb - ND - 1 > 1 ? nb - ND - 1 : 1;  // column blocks that have a far field at all
     // groups are independent pipelines; split them over launches if there are more groups than SMs / 3

@@ -1228,13 +1228,13 @@ size_t workspace_bytes(int T, int N) {
     return kHeaderBytes + rowtable_bytes(T, N) + partial_bytes(T, N) + uflag_bytes(T) + bflag_bytes() + scratch_bytes(N);
 }
 
-int sweep(const float *score, const float *noise, int T, int N, int direction, int flags, void *workspace,
-          uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream_) {
+int sweep(const float *score, long long pitch, const float *noise, int T, int N, int direction, int flags,
+          void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!score || !workspace || T < 1 || N < 1 || (T > 1 && !noise) || epoch == 0 ||
         (direction != TKB_BACKWARD && direction != TKB_FORWARD) ||
         (flags & ~(TKB_SWEEP_VITERBI | TKB_SWEEP_LOGSUM)) || flags == 0 ||
-        ((flags & TKB_SWEEP_VITERBI) && !out_code) || (long long)T * T >= (1ll << 40)) {
+        ((flags & TKB_SWEEP_VITERBI) && !out_code) || (long long)T * T >= (1ll << 40) || pitch < N) {
         set_error("tkb_semicrf_sweep[strip]: invalid argument (T=%d N=%d dir=%d flags=%d epoch=%u)", T, N, direction,
                   flags, epoch);
         return TKB_EINVAL;
@@ -1268,19 +1268,20 @@ int sweep(const float *score, const float *noise, int T, int N, int direction, i
     p.timeline = g_timeline;
     if (direction == TKB_BACKWARD) {
         p.Sbase = score;
-        p.sx = N;
-        p.sy = (long long)T * N;
+        p.sx = pitch;
+        p.sy = (long long)T * pitch;
         p.etabase = noise;
         p.se = N;
     } else {
-        p.Sbase = score + ((long long)(T - 1) * T + (T - 1)) * N;
-        p.sx = -(long long)T * N;
-        p.sy = -(long long)N;
+        p.Sbase = score + ((long long)(T - 1) * T + (T - 1)) * pitch;
+        p.sx = -(long long)T * pitch;
+        p.sy = -(long long)pitch;
         p.etabase = noise ? noise + (long long)(T - 2) * N : nullptr;  // skip weight of x is noise[T-2-x]
         p.se = -(long long)N;
     }
     const uintptr_t addr = reinterpret_cast<uintptr_t>(score);
-    const int align = (N % 4 == 0 && (addr & 15) == 0) ? 16 : ((N % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
+    // the track pitch, not N, decides the copy width: a padded score tensor (pitch % 4 == 0) takes the 16-byte path
+    const int align = (pitch % 4 == 0 && (addr & 15) == 0) ? 16 : ((pitch % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
     // groups are independent pipelines; a launch holds up to two track ranges, its other SMs run strip CTAs
     // (all CTAs of a launch must be co-resident: one per SM)
     p.SN = (G < kGroupsPerLaunch ? G : kGroupsPerLaunch) * NG;

@@ -12,45 +12,68 @@
 
 namespace tkb {
 
-// grid: (ceil(T*N / (256*VEC)), T); row e = blockIdx.y; threads sweep (b, n) contiguously.
+// Marginal writer.  Row e = blockIdx.y; a block covers MB_COLS consecutive begins b.  A thread owns one vector of VEC
+// tracks (its beta[e] - logZ and grad_output stay in registers) and walks the begins of its sub-row: no division,
+// one score load, one alpha load (L1/L2-resident, [T,N]) and one store per vector; everything above the diagonal
+// is a plain zero store (the API returns a dense gradient).
+constexpr int MB_THREADS = 256;
+constexpr int MB_COLS = 64;
 template <int VEC>
-__global__ void __launch_bounds__(256) marginals_kernel(const float *__restrict__ score, const float *__restrict__ alpha,
-                                                        const float *__restrict__ beta, const float *__restrict__ gscale,
-                                                        int T, int N, float *__restrict__ grad) {
+__global__ void __launch_bounds__(MB_THREADS) marginals_kernel(const float *__restrict__ score,
+                                                              const float *__restrict__ alpha,
+                                                              const float *__restrict__ beta,
+                                                              const float *__restrict__ gscale, int T, int N,
+                                                              float *__restrict__ grad) {
     const int e = blockIdx.y;
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;  // index into (b, n)
-    if (i0 >= (long long)T * N) return;
-    const long long base = (long long)e * T * N + i0;
+    const int nv = (N + VEC - 1) / VEC;            // vectors per cell
+    const int rows = MB_THREADS / nv > 0 ? MB_THREADS / nv : 1;  // begins handled side by side
+    const int b_begin = blockIdx.x * MB_COLS;
+    const int b_end = min(b_begin + MB_COLS, T);
     const float *logZ = alpha + (long long)(T - 1) * N;  // :417
-    float out[VEC];
-    float sv[VEC];
-    const int b0 = (int)(i0 / N);
-    if (b0 > e) {  // whole vector above the diagonal (VEC divides N, so a vector never straddles b)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) out[v] = 0.0f;
-    } else {
-        if (VEC == 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(score + base);
-            sv[0] = t.x; sv[1] = t.y; sv[2] = t.z; sv[3 % VEC] = t.w;
-        } else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) sv[v] = score[base + v];
-        }
+    for (int v0 = threadIdx.x; v0 < rows * nv; v0 += MB_THREADS) {  // (one pass unless nv > MB_THREADS)
+        const int sub = v0 / nv, n0 = (v0 - sub * nv) * VEC;
+        float ce[VEC], gs[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const int n = (int)((i0 + v) % N);
-            float x = alpha[(long long)b0 * N + n] + ((beta[(long long)e * N + n] - logZ[n]) + sv[v]);  // :424
-            if (b0 == e) x -= 2.0f * softplus_ref(sv[v]);                                               // :427
-            float g = __expf(x);                                                                        // :438
-            if (gscale) g *= gscale[n];                                                                 // :472
-            out[v] = g;
+            const int n = n0 + v;
+            ce[v] = n < N ? (beta[(long long)e * N + n] - logZ[n]) : 0.0f;
+            gs[v] = (gscale && n < N) ? gscale[n] : 1.0f;
         }
-    }
-    if (VEC == 4) {
-        *reinterpret_cast<float4 *>(grad + base) = make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]);
-    } else {
+        for (int b = b_begin + sub; b < b_end; b += rows) {
+            const long long base = ((long long)e * T + b) * N + n0;
+            float out[VEC];
+            if (b > e) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) grad[base + v] = out[v];
+                for (int v = 0; v < VEC; ++v) out[v] = 0.0f;
+            } else {
+                float sv[VEC], av[VEC];
+                if (VEC == 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(score + base);
+                    const float4 a = *reinterpret_cast<const float4 *>(alpha + (long long)b * N + n0);
+                    sv[0] = t.x; sv[1 % VEC] = t.y; sv[2 % VEC] = t.z; sv[3 % VEC] = t.w;
+                    av[0] = a.x; av[1 % VEC] = a.y; av[2 % VEC] = a.z; av[3 % VEC] = a.w;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        sv[v] = (n0 + v < N) ? score[base + v] : 0.0f;
+                        av[v] = (n0 + v < N) ? alpha[(long long)b * N + n0 + v] : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float x = av[v] + (ce[v] + sv[v]);               // :424
+                    if (b == e) x -= 2.0f * softplus_ref(sv[v]);    // :427
+                    out[v] = __expf(x) * gs[v];                     // :438, :472
+                }
+            }
+            if (VEC == 4) {
+                *reinterpret_cast<float4 *>(grad + base) = make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (n0 + v < N) grad[base + v] = out[v];
+            }
+        }
     }
 }
 
@@ -130,14 +153,12 @@ extern "C" int tkb_semicrf_marginals(const float *score, const float *noise, int
     if (out_grad) {
         const bool v4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(score) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(out_grad) & 15) == 0);
-        const long long per_row = (long long)T * N;
-        if (v4) {
-            dim3 grid((unsigned)((per_row / 4 + 255) / 256), (unsigned)T);
-            marginals_kernel<4><<<grid, 256, 0, stream>>>(score, alpha, beta, gscale, T, N, out_grad);
-        } else {
-            dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)T);
-            marginals_kernel<1><<<grid, 256, 0, stream>>>(score, alpha, beta, gscale, T, N, out_grad);
-        }
+        const bool a4 = v4 && ((reinterpret_cast<uintptr_t>(alpha) & 15) == 0);
+        dim3 grid((unsigned)((T + MB_COLS - 1) / MB_COLS), (unsigned)T);
+        if (a4)
+            marginals_kernel<4><<<grid, MB_THREADS, 0, stream>>>(score, alpha, beta, gscale, T, N, out_grad);
+        else
+            marginals_kernel<1><<<grid, MB_THREADS, 0, stream>>>(score, alpha, beta, gscale, T, N, out_grad);
         TKB_CUDA(cudaGetLastError());
     }
     if (out_grad_noise && T > 1) {

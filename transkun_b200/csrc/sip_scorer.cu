@@ -92,7 +92,8 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
 
 struct ScorerParams {
     const float *q, *k, *diag;  // [NT][T][D], [NT][T][D], [NT][T]
-    float *out;                 // [T][T][NT]
+    float *out;                 // [T][T][pitch], the first NT tracks of a cell are written
+    long long pitch;
     int NT, T, D;
     float qscale;               // 1/sqrt(D)
     int tiles_b_total;          // helper for tile decoding
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sip_scorer_kernel(const ScorerP
     // epilogue: warp w reads TMEM lanes 32*(w%4).., warps 0-3 take begins 0..31 of the tile, warps 4-7 begins 32..63
     const int e = e0 + 32 * (warp & 3) + lane;
     const int jbase = (warp >> 2) * 32;
-    const bool vec_ok = (NT % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool vec_ok = (p.pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     float dg[SC_NG];
 #pragma unroll
     for (int t = 0; t < SC_NG; ++t) dg[t] = (e < T && t < ntrk) ? p.diag[(size_t)(n0 + t) * T + e] : 0.0f;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sip_scorer_kernel(const ScorerP
                     const float len = (float)(e - b);
 #pragma unroll
                     for (int t = 0; t < SC_NG; ++t) v[t] = (b == e) ? dg[t] : (acc[t][jj] * p.qscale) * len;
-                    float *o = p.out + ((size_t)e * T + b) * NT + n0;
+                    float *o = p.out + ((size_t)e * T + b) * p.pitch + n0;
                     if (vec_ok && ntrk == SC_NG) {
                         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
@@ -266,7 +267,12 @@ using namespace tkb;
 
 extern "C" int tkb_sip_score(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
                              float *out_score, void *stream_) {
-    if (!q || !k || !diag || !out_score || n_tracks < 1 || T < 1 || D < SC_KC || D % SC_KC != 0 ||
+    return tkb_sip_score_pitched(q, k, diag, n_tracks, T, D, out_score, n_tracks, stream_);
+}
+
+extern "C" int tkb_sip_score_pitched(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
+                                     float *out_score, int64_t pitch, void *stream_) {
+    if (!q || !k || !diag || !out_score || n_tracks < 1 || T < 1 || D < SC_KC || D % SC_KC != 0 || pitch < n_tracks ||
         (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15)) {
         set_error("tkb_sip_score: invalid argument (tracks=%d T=%d D=%d; D must be a multiple of 32, q/k 16-byte aligned)",
                   n_tracks, T, D);
@@ -283,6 +289,7 @@ extern "C" int tkb_sip_score(const float *q, const float *k, const float *diag, 
     p.diag = diag;
     p.out = out_score;
     p.NT = n_tracks;
+    p.pitch = pitch;
     p.T = T;
     p.D = D;
     p.qscale = 1.0f / sqrtf((float)D);
