@@ -13,12 +13,8 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libtranskun_b200.so")
 INCLUDE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "shared",  # same libcudart the host process (PyTorch) already loaded
-]
+# flags: -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC; linked -shared with
+# -cudart shared (the same libcudart the host process, PyTorch, already loaded)
 
 
 def sources():
@@ -33,18 +29,36 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """Compiles every .cu to an object file in parallel (the two sweep kernels dominate), then links."""
     if not force and out == LIB and not needs_build():
         return LIB
+    import concurrent.futures
+    import tempfile
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-o", out, *sources(), "-lcufft"]
+    common = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+              *[f"-D{d}" for d in defines], "-I", INCLUDE]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        common[1:1] = ["-Xptxas", "-v"]
+    log = []
+    with tempfile.TemporaryDirectory(prefix="tkb_obj_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            res = subprocess.run([*common, "-c", src, "-o", obj], capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join([*common, "-c", src]) + "\n" + res.stdout + res.stderr)
+            return obj, res.stderr
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = []
+            for obj, err in ex.map(compile_one, sources()):
+                objs.append(obj)
+                log.append(err)
+        link = [nvcc, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs,
+                "-lcufft"]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("".join(log))
     return out
 
 

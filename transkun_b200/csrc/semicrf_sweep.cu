@@ -476,6 +476,7 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
     const int n = n0 + tr;
     const int c = lane;
     const int ptrk = qd * NQ + tr;  // track inside the group
+    (void)epoch;
     // accumulators: [0] the block on the chain, [d] the block d below it
     float best[ND + 1], lM[ND + 1], lS[ND + 1];
     int bsel[ND + 1];

@@ -1,36 +1,28 @@
-// semicrf_sweep.cu -- the semi-Markov dynamic programme as ONE persistent kernel (solver / helper CTAs).
+// semicrf_sweep_strip.cu -- the semi-Markov dynamic programme, STRIP design (experimental: TKB_SWEEP=strip).
 //
-// Replaces the TorchScript step loops of the reference
-// (transkun/CRF/NeuralSemiCRFInterval.py:31-51, :124-144, :218-234, :303-327):
-//     q[x] = ( skip(x)  (+)  (+)_{y>x} q[y] (x) S(y,x) )  (x)  unary(x)
-// over the (max,+) semiring (Viterbi, bit-exact fp32: one add per candidate, exact max, the
-// reference's tie order) and the (logsumexp,+) semiring (log-partition), both fed by a single
-// read of the score triangle.
-//
-// Mirrored coordinates.  x is the position being solved, y > x a solved one.
-//   BACKWARD: x = begin b, y = end e, S(y,x) = score[e][b]      (sx = N,    sy = T*N)
-//   FORWARD : x = T-1-end, y = T-1-begin, S(y,x) = score[T-1-x][T-1-y]
-//                                                               (sx = -T*N, sy = -N)
-// so one kernel serves viterbiBackward/beta and viterbi/alpha.
-//
-// It is a lower-triangular solve: T strictly sequential steps per track.  The design keeps that
-// chain inside ONE SM from the first to the last position, and lets every other SM stream the
-// triangle:
-//   * tracks are independent; a GROUP is 8 tracks = one 32-byte sector of the track-innermost layout;
-//   * per group two SOLVER CTAs (4 tracks = 16 bytes each) run the chain: one warp per track, lane =
-//     column of the current 32-column block, V and L semirings interleaved in the same instruction
-//     stream.  A chain step broadcasts the just-finished row with shuffles and pushes it into the
-//     current block (the diagonal tile, on the chain) and into the next ND blocks (off the chain); the
-//     score values come from a shared-memory ring of "row bands" (32 rows x (ND+1)*32 columns x 16 B)
-//     that four loader warps of the same CTA keep filled with cp.async, mbarrier-synchronised;
-//   * per group H HELPER CTAs own the column blocks round-robin and stream everything further than ND
-//     blocks above the diagonal (the bulk of the bytes): 16 warps, each every 16th pair of rows,
-//     cp.async FIFOs, register accumulators, merged once per block and handed to the solvers as a
-//     "far partial";
-//   * rows travel solver -> helpers through a global-memory mailbox of 64-bit words {fp32 value, epoch},
-//     far partials travel helper -> solver the same way: one relaxed store publishes, one relaxed load
-//     observes (no fence, no flag, no reset; the epoch grows with every launch).
-// All CTAs of a launch must be co-resident (cooperative launch).
+// Same contract, same ABI and same parity ladder as semicrf_sweep.cu (see there for the recurrence, the mirrored
+// coordinates and the reference lines it replaces); a different decomposition, built on what round 1 measured
+// (profiles/r01_sweep_experiments.txt):
+//   * the track-innermost layout gives a CTA that owns 8 tracks one 32-byte sector per cell; a CTA that owns a
+//     32-column strip for ALL tracks of a range reads whole contiguous rows.  STRIP CTAs (every SM that is not a
+//     solver) process units (range, column block J, row class k): thread <-> (column, 4 tracks), one 16-byte
+//     cp.async per row and thread into its own FIFO slot (a warp covers 512 contiguous bytes), 4 rows per stage,
+//     {max, argmax, M, S} in registers for the whole unit.  The solved rows of a stage come from a plain-float row
+//     table [T][2][Npad] by cp.async.bulk copies into a shared ring behind mbarriers (one row warp per CTA);
+//     validity is one flag per 32-row block, written by the publisher after a fence.  Unit partials go to a
+//     [block][class][word][track][column] buffer with a flag per unit; the solver's prep warp merges the classes;
+//   * the near band (rows within ND blocks of the diagonal) is copied by the same units, transposed through the
+//     FIFO, into an L2-resident ring laid out per track, so that a solver loads its bands with coalesced 16-byte
+//     copies instead of a sector gather that shares the LSU pipe with its own chain warps;
+//   * SOLVER CTAs own 2 tracks: one chain warp per (track, semiring), each alone on an SMSP, lane = column.
+//     Columns are solved in micro-blocks of four, redundantly in every lane's registers (values only: the Viterbi
+//     argmax stays in the owner lane's push, so the reference's tie order is untouched); the log-sum chain keeps
+//     the scale M of a pair on a max-plus recursion of its own, so every exponent is known from the M's alone and
+//     the S's follow with fused multiply-adds whose weights are <= 1.  A prep warp stages per-column constants and
+//     the merged far partial, publisher warps do every global store: a chain warp touches shared memory only.
+// Today this design is slower than the default (425 vs 269 us at T=2048, N=88): each unit's last stage needs the
+// chain to have finished block J+ND+1 and its CTA idles there, and the hand-over flag -> ring -> stage -> partial
+// -> flag -> merge is ~15 us against a 2 us block.  All CTAs of a launch must be co-resident (cooperative launch).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -63,7 +55,6 @@ constexpr int NCONW = NCT / 32;    // consumer warps of a strip CTA
 constexpr int NQW = 1;             // + the row warp (bulk copies of solved rows into a shared ring)
 constexpr int NW = NCONW + NQW;    // warps per CTA (every role)
 constexpr int NT = NW * 32;        // 768 threads
-constexpr int NQS = 4;             // mailbox ring stages (tagged words in flight)
 #ifndef TKB_NQF
 #define TKB_NQF 16
 #endif
@@ -79,7 +70,7 @@ constexpr int PR_DR = 0, PR_ETA = 32, PR_FARV = 64, PR_FARS = 96, PR_SP2 = 128, 
 // the near-tile and partial transposes) | tagged mailbox rows [NSTG][4][2 kinds][TRK] u64 | untagged rows
 // [NSTG][4][2][TRK] float
 constexpr size_t kFifoBytes = (size_t)NSTG * 4 * NCT * 16;
-constexpr size_t kQTagBytes = 0;
+constexpr size_t kQTagBytes = 0;  // (the tagged-word staging ring of the mailbox variant is gone)
 constexpr size_t kQValBytes = (size_t)NQF * 4 * 2 * TRK * 4;
 constexpr size_t kStripSmem = kFifoBytes + kQTagBytes + kQValBytes + 2 * NQF * 8;
 // solver shared memory: row bands [NBAND][NQ tracks][BX rows][BANDCOLS] (planar per track: a chain warp reads
@@ -363,6 +354,7 @@ __device__ __forceinline__ void strip_role(const SweepParams &p, unsigned char *
         const int ntq = min(4, ntr - 4 * quad);          // tracks of my quad that exist
         const float *pbase = p.Sbase + (long long)(x0 + col) * p.sx + n_lo + 4 * quad;  // + y * sy
         const int uord = (u - h) / nstrip;  // diagnostics: ordinal of this unit in my list
+        (void)uord;
         if (t == 0) TKB_STAMP(uord, 0);
         auto load_piece = [&](unsigned dst, int y, bool ok) {  // my 16 bytes of row y (zero-filled if !ok)
             const float *src = ok ? pbase + (long long)y * p.sy : p.Sbase;
@@ -657,10 +649,10 @@ template <int DIR>
 __device__ __forceinline__ void chain_viterbi(const SweepParams &p, unsigned char *smem_raw, const SolverSmem &sm,
                                               int g, int ptrk, int tr) {
     const int c = threadIdx.x & 31;
-    const int T = p.T, N = p.N;
+    const int T = p.T;
     const int nb = (T + BX - 1) / BX;
-    const int n = g * NG + ptrk;
-    const unsigned epoch = p.epoch;
+    (void)g;
+    (void)ptrk;
     const float *bands = reinterpret_cast<const float *>(smem_raw);
     const float *preps = bands + (size_t)NBAND * (kBandBytes / 4);
     float best[ND + 1];
@@ -678,7 +670,6 @@ __device__ __forceinline__ void chain_viterbi(const SweepParams &p, unsigned cha
         if (it >= 2) mbar_wait(sm.pub_empty + (cwi * 2 + (it & 1)) * 8, ((it >> 1) - 1) & 1, p.status);
         const int x0 = j * BX, x = x0 + c;
         const int ncols = min(BX, T - x0);
-        const bool active = x < T;
         if (c == 0 && tr == 0) TKB_CSTAMP(it, 3);
         mbar_wait(sm.prep_full + ps * 8, (it / NPREP) & 1, p.status);
         const float *pr = preps + (size_t)(ps * NQ + tr) * PR_FLOATS;
@@ -780,10 +771,10 @@ template <int DIR>
 __device__ __forceinline__ void chain_logsum(const SweepParams &p, unsigned char *smem_raw, const SolverSmem &sm,
                                              int g, int ptrk, int tr) {
     const int c = threadIdx.x & 31;
-    const int T = p.T, N = p.N;
+    const int T = p.T;
     const int nb = (T + BX - 1) / BX;
-    const int n = g * NG + ptrk;
-    const unsigned epoch = p.epoch;
+    (void)g;
+    (void)ptrk;
     const float *bands = reinterpret_cast<const float *>(smem_raw);
     const float *preps = bands + (size_t)NBAND * (kBandBytes / 4);
     float lM[ND + 1], lS[ND + 1];
@@ -800,7 +791,6 @@ __device__ __forceinline__ void chain_logsum(const SweepParams &p, unsigned char
         if (it >= 2) mbar_wait(sm.pub_empty + (cwi * 2 + (it & 1)) * 8, ((it >> 1) - 1) & 1, p.status);
         const int x0 = j * BX, x = x0 + c;
         const int ncols = min(BX, T - x0);
-        const bool active = x < T;
         if (c == 0 && tr == 0) TKB_CSTAMP(it, 0);
         mbar_wait(sm.prep_full + ps * 8, (it / NPREP) & 1, p.status);
         const float *pr = preps + (size_t)(ps * NQ + tr) * PR_FLOATS;
