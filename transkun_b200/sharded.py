@@ -89,3 +89,58 @@ def split_records(rec: torch.Tensor):
     """(counts [N] int32, logZ [N] fp32, pairs [N, 2T, 2] int32) views of gathered records."""
     T4 = rec.shape[1] - 2
     return rec[:, 0], rec[:, 1].view(torch.float32), rec[:, 2:].view(rec.shape[0], T4 // 2, 2)
+
+
+class PushGather:
+    """All-gather of the per-track records by copy engines, overlapped with the next step's sweep.
+
+    The NCCL all-gather is latency-bound (a few MB) but its kernel cannot share the GPU with the cooperative sweep
+    launch, which wants 143 of the 148 SMs at once: at 8 GPUs the exchange costs a third of a step.  Here every rank
+    PUSHES its block into a symmetric (peer-mapped, NVLink) buffer of every other rank with plain device-to-device
+    copies on a side stream -- DMA engines, no SMs -- followed by one signal-pad barrier (a one-CTA kernel), while the
+    compute stream is already running the next sweep.  Buffers are double-buffered by step parity.  Requires every
+    rank to own the same number of tracks and torch's symmetric memory (same node, P2P): `available()` says so, and
+    callers fall back to `gather_records` otherwise."""
+
+    def __init__(self, n_local: int, record_len: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.shape = (2, self.world, n_local, record_len)
+        self.buf = symm_mem.empty(self.shape, dtype=torch.int32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.peers = [self.hdl.get_buffer(r, self.shape, torch.int32) for r in range(self.world)]
+        self.comm = torch.cuda.Stream(device=device)
+        self.done = [None, None]  # per slot: event after which the slot holds a complete gather
+        self.step = 0
+        self.hdl.barrier(channel=0)
+
+    def submit(self, rec: torch.Tensor) -> int:
+        """Start the exchange of this step's records; returns the slot that will hold [world, n_local, R]."""
+        slot = self.step & 1
+        self.step += 1
+        cur = torch.cuda.current_stream(rec.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        rec.record_stream(self.comm)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            # everyone has reached this submit, i.e. is done with the result this slot held two steps ago
+            self.hdl.barrier(channel=2 + slot)
+            for r in range(self.world):  # my block into everyone's buffer (including mine)
+                self.peers[(self.rank + r) % self.world][slot, self.rank].copy_(rec, non_blocking=True)
+            self.hdl.barrier(channel=slot)  # every rank's pushes of this step have landed everywhere
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+        self.done[slot] = ev
+        return slot
+
+    def result(self, slot: int) -> torch.Tensor:
+        """[world * n_local, R] records of the step submitted into `slot` (valid once the current stream passed wait())."""
+        return self.buf[slot].view(self.world * self.shape[2], self.shape[3])
+
+    def wait(self) -> None:
+        cur = torch.cuda.current_stream()
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
