@@ -1,10 +1,15 @@
+"""Fused / single-semiring sweep timing over shapes (CUDA events).  usage: python scripts/sweep_shapes.py [T,N ...]
+(negative N: the same N with the track axis padded to a multiple of 4)."""
 import sys
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import torch
 from golden_util import make_inputs
 from transkun_b200.CRF.NeuralSemiCRFInterval import sweep
 from transkun_b200._lib import BACKWARD, FORWARD, SWEEP_LOGSUM, SWEEP_VITERBI
-for T, N in ((691, 88), (691, 90), (691, -90), (691, 360)):  # negative N: padded track axis
+SHAPES = [(691, 88), (691, 90), (691, -90), (691, 360)]  # negative N: padded track axis
+if len(sys.argv) > 1:
+    SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+for T, N in SHAPES:
     padded, N = N < 0, abs(N)
     score, noise = make_inputs("randn", T, N, 3)
     s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
