@@ -10,15 +10,18 @@ streams it from HBM; no explicit L2 flush needed) -- the configuration the metri
 cells = T^2 * N per step.
 
 value    : whole-job cells/s with inputs resident in HBM (CUDA events, max over ranks).
-e2e      : same metric through the public API (NeuralSemiCRFInterval.decodeWithLogZ) with HOST inputs:
-           pinned H2D of score/noise and D2H of the decoded intervals + logZ inside the timed region.
+e2e      : same metric through the public API from HOST inputs (NeuralSemiCRFInterval.fromHost(...).decodeWithLogZ()):
+           pinned H2D of the part of score the semi-CRF reads (end >= begin) and of noise, D2H of the decoded
+           intervals + logZ, and the construction of the Python interval lists, all inside the timed region.
 roofline : dominant kernel (sweep) algorithmic bytes 4*N*T(T+1)/2 per launch / its CUDA-event duration,
-           against MEASURED_PEAKS.json's HBM copy bandwidth.
+           against MEASURED_PEAKS.json's HBM copy bandwidth; traffic = DRAM bytes of the committed ncu capture.
 cpu_baseline / --impl reference : the reference is pure Python/PyTorch and cannot travel to the GPU box,
            so the CPU arm is the C/OpenMP oracle port (oracle/, checked against the reference's golden
            outputs) on all host cores.
-Multi-GPU: tracks shard with no data-path collective (weak scaling: every rank owns its own 88 tracks);
-           one NCCL all-gather of the packed intervals per step.
+Multi-GPU: tracks shard with no data-path collective (weak scaling: every rank owns its own 88 tracks); the only
+           exchange is the all-gather of the packed intervals: copy-engine pushes into symmetric NVLink peer memory on a
+           side stream, overlapped with the next step's sweep (transkun_b200.sharded.PushGather; NCCL all-gather
+           per step as the fallback, TKB_GATHER=nccl to force it).
 """
 import argparse
 import json
