@@ -48,7 +48,10 @@ constexpr int BX = 32;     // columns per block (= lanes of a chain warp)
 constexpr int ND = TKB_ND;  // blocks above the diagonal block that the solver pushes itself
 constexpr int NBAND = (ND == 2) ? 4 : 3;  // row bands resident in a solver CTA
 constexpr int BANDCOLS = (ND + 1) * BX;
-constexpr int NW = 16;     // warps per CTA (helper: 16 row slices; solver: 4 chain + 4 loader warps)
+#ifndef TKB_NW
+#define TKB_NW 16
+#endif
+constexpr int NW = TKB_NW;  // warps per CTA (helper: NW row slices; solver: chain, loader, publisher warps)
 constexpr int NT = NW * 32;
 constexpr int NCW = NQ;    // chain warps
 constexpr int NLW = 4;     // loader warps
@@ -405,8 +408,10 @@ __device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char 
         const int c = lane;
         unsigned long long *dst =
             p.part + ((((size_t)g * nb + J) * 2 + (s_is_lse ? 1 : 0)) * NG + sn) * (BX * 2) + 2 * c;
-        if (!s_is_lse && DO_V) {
-            // branch-free 16-way merge: the maximum, then among the partials that attain it the row the
+        if (warp >= 16) {
+            // (more than 16 row slices: the extra warps have nothing to merge)
+        } else if (!s_is_lse && DO_V) {
+            // branch-free NW-way merge: the maximum, then among the partials that attain it the row the
             // reference's candidate order prefers (BACKWARD: smallest y, FORWARD: largest y).  Empty partials
             // are (-inf, -1); (unsigned)-1 is the largest unsigned, so they never win the min.
             float pv[NW];
