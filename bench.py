@@ -222,6 +222,11 @@ def run_ours(args):
             if rank == 0:
                 print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
             push = None
+    if world > 1:  # every rank must take the same path
+        agree = torch.tensor([1 if push is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            push = None
 
     def step(record=False):
         if record:

@@ -109,7 +109,10 @@ class PushGather:
         self.shape = (2, self.world, n_local, record_len)
         self.buf = symm_mem.empty(self.shape, dtype=torch.int32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        self.peers = [self.hdl.get_buffer(r, self.shape, torch.int32) for r in range(self.world)]
+        peers = [self.hdl.get_buffer(r, self.shape, torch.int32) for r in range(self.world)]
+        # destination views, built once (the per-step host work is on the critical path of a 0.3 ms step): my block in
+        # the buffer of rank (me + k) % world, for both slots
+        self.dst = [[peers[(self.rank + k) % self.world][slot, self.rank] for k in range(self.world)] for slot in (0, 1)]
         self.comm = torch.cuda.Stream(device=device)
         self.done = [None, None]  # per slot: event after which the slot holds a complete gather
         self.step = 0
@@ -127,8 +130,8 @@ class PushGather:
             self.comm.wait_event(ready)
             # everyone has reached this submit, i.e. is done with the result this slot held two steps ago
             self.hdl.barrier(channel=2 + slot)
-            for r in range(self.world):  # my block into everyone's buffer (including mine)
-                self.peers[(self.rank + r) % self.world][slot, self.rank].copy_(rec, non_blocking=True)
+            for d in self.dst[slot]:  # my block into everyone's buffer (including mine)
+                d.copy_(rec, non_blocking=True)
             self.hdl.barrier(channel=slot)  # every rank's pushes of this step have landed everywhere
             ev = torch.cuda.Event()
             ev.record(self.comm)
