@@ -881,9 +881,9 @@ using namespace tkb;
 
 extern "C" size_t tkb_sweep_workspace_bytes(int T, int N) {
     if (T < 1 || N < 1) return 0;
-    const size_t v2 = kHeaderBytes + mailbox_bytes(T, N) + partial_bytes(T, N);
-    const size_t v3 = strip::workspace_bytes(T, N);
-    return v2 > v3 ? v2 : v3;
+    // the design in use is fixed for the life of the process (TKB_SWEEP), so is the layout of its workspace
+    if (use_strip()) return strip::workspace_bytes(T, N);
+    return kHeaderBytes + mailbox_bytes(T, N) + partial_bytes(T, N);
 }
 
 extern "C" int tkb_semicrf_sweep(const float *score, const float *noise, int T, int N, int direction, int flags,
