@@ -1,13 +1,11 @@
-"""Diagnostics: free-running time of the sweep's two roles.
-
-A launch that reuses the previous launch's epoch finds every mailbox word and every far partial already
-valid, so nobody ever waits: its duration is max(chain alone, far-field streaming alone) -- which of the two
-bounds the real (dependent) launch.  Results are identical (same values rewritten).
+"""Free-running time of the sweep kernel: a launch that re-uses the previous launch's epoch finds every mailbox word and
+far partial already valid, so nobody waits -- the duration is the slower role's own pace.  CUDA events around the bare
+C-ABI call (outputs preallocated).  With the diagnostics build (TKB_LIBRARY=..._timeline.so) TKB_DBG selects ablations:
+1 = streaming CTAs skip the arithmetic, 2 = skip the score prefetch, 4 = no timeline stamps (always set here).
 usage: python scripts/replay.py [T] [N] [flags]"""
+import ctypes
 import os
 import sys
-
-os.environ.setdefault("TKB_SWEEP", "strip")  # these diagnostics target the strip design
 
 import torch
 
@@ -15,45 +13,51 @@ sys.path.insert(0, "tests")
 sys.path.insert(0, ".")
 from golden_util import make_inputs  # noqa: E402
 from transkun_b200 import _lib  # noqa: E402
-from transkun_b200._lib import BACKWARD, SWEEP_LOGSUM, SWEEP_VITERBI  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 88
-flags = int(sys.argv[3]) if len(sys.argv) > 3 else (SWEEP_VITERBI | SWEEP_LOGSUM)
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 L = _lib.load()
 score, noise = make_inputs("randn", T, N, 1234)
 s, z = torch.from_numpy(score).cuda(), torch.from_numpy(noise).cuda()
 ws = torch.zeros(L.tkb_sweep_workspace_bytes(T, N), dtype=torch.uint8, device="cuda")
 code = torch.empty((N, T), dtype=torch.int32, device="cuda")
 lse = torch.empty((T, N), dtype=torch.float32, device="cuda")
-st = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.current_stream().cuda_stream
 
 
-def run(epoch):
-    rc = L.tkb_semicrf_sweep(s.data_ptr(), z.data_ptr(), T, N, BACKWARD, flags, ws.data_ptr(), epoch,
-                             code.data_ptr(), None, lse.data_ptr(), st)
+def launch(epoch):
+    rc = L.tkb_semicrf_sweep(s.data_ptr(), z.data_ptr(), T, N, 0, flags, ws.data_ptr(), epoch, code.data_ptr(), None,
+                             lse.data_ptr(), stream)
     _lib.check(rc, "sweep")
 
 
-def timed(fn, reps=10):
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
-        fn(i)
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ts = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(reps))
-    return ts[len(ts) // 2], ts[0]
+def timed(epoch, reps=5):
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch(epoch)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3)
+    return best
 
 
-for e in range(1, 4):
-    run(e)
+for e in (1, 2, 3):
+    launch(e)
 torch.cuda.synchronize()
-ref_code, ref_lse = code.clone(), lse.clone()
-med, best = timed(lambda i: run(10 + i))
-print(f"dependent launches : median {med:.1f} us, best {best:.1f} us")
-med, best = timed(lambda i: run(19))
-print(f"replay (same epoch): median {med:.1f} us, best {best:.1f} us  (no waits: max of chain-only / stream-only)")
-# (a replayed launch reads recycled ring slots: its results are not meaningful, only its duration)
-alg = 4.0 * N * T * (T + 1) / 2
-print(f"algorithmic bytes {alg / 1e6:.1f} MB -> replay {alg / med / 1e3:.0f} GB/s")
+dep = []
+for e in range(4, 9):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch(e)
+    e1.record()
+    torch.cuda.synchronize()
+    dep.append(e0.elapsed_time(e1) * 1e3)
+print(f"T={T} N={N} flags={flags}: dependent launch {min(dep):.1f} us (best of 5), replay {timed(8):.1f} us", flush=True)
+if hasattr(L, "tkb_debug_set_flags"):
+    for dbg in (5, 6, 7, 15, 31, 63, 68):
+        L.tkb_debug_set_flags(dbg)
+        print(f"   replay with debug flags {dbg} (1 no arithmetic, 2 no score prefetch, 4 no stamps, 8 no mailbox handshake, 16 no mailbox producers, 32 consumers leave at once, 64 solver CTAs only): {timed(8):.1f} us", flush=True)
+    L.tkb_debug_set_flags(4)

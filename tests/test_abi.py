@@ -33,16 +33,11 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_sizes(lib):
     assert lib.tkb_version() == 1
-    # the workspace of the sweep design in use (TKB_SWEEP=strip selects the experimental one):
-    #   solver/helper: header + row mailbox (2 semirings * T * ceil8(N) words) + far partials
-    #   strip        : header + solved rows + block flags + far partials + unit/band flags + near-band ring
-    a256 = lambda x: (x + 255) // 256 * 256
+    # sweep workspace: header + row mailbox (4 replicas * 2 semirings * T * ceil8(N) words) + far partials
+    # ([blocks][2 semirings][ceil8(N)][32 columns][2] words)
     def ws(T, N):
-        npad, nb, G = (N + 7) // 8 * 8, (T + 31) // 32, (N + 7) // 8
-        v2 = 256 + 2 * T * npad * 8 + G * nb * 2 * 8 * 32 * 2 * 8
-        strip = (256 + a256(2 * T * npad * 4) + a256(2 * nb * npad * 4) + a256(nb * 8 * 4 * npad * 32 * 4)
-                 + a256(nb * 8 * 2 * 8) + a256(2 * 16 * 3 * 8 * 8) + 16 * min(npad, 176) * 32 * 96 * 4)
-        return strip if os.environ.get("TKB_SWEEP", "").startswith("s") else v2
+        npad, nb = (N + 7) // 8 * 8, (T + 31) // 32
+        return 256 + 4 * 2 * T * npad * 8 + nb * 2 * npad * 32 * 2 * 8
     assert lib.tkb_sweep_workspace_bytes(2048, 88) == ws(2048, 88)
     assert lib.tkb_sweep_workspace_bytes(10, 9) == ws(10, 9)
     assert lib.tkb_sweep_workspace_bytes(300, 1200) == ws(300, 1200)

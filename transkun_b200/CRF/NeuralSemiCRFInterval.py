@@ -66,6 +66,21 @@ def _workspace(T: int, N: int, device: torch.device, slot: int = 0) -> _Workspac
     return ws
 
 
+def _raise_if_flagged(ws: Optional["_Workspace"]):
+    """The status word of a sweep workspace holds the epoch of a launch whose inter-CTA wait timed out (0 if none
+    ever did): only the launch that failed is flagged, the workspace stays usable.  Synchronises."""
+    if ws is not None and ws.epoch != 0 and (int(ws.buf[:4].view(torch.int32).item()) & 0xFFFFFFFF) == ws.epoch:
+        raise _lib.TkbError("semi-CRF sweep: an inter-CTA wait timed out; results are invalid")
+
+
+def _poison_if_flagged(ws: "_Workspace", out: torch.Tensor) -> torch.Tensor:
+    """Same check without a synchronisation, for results that stay on the device (log Z, log-probabilities): if
+    the launch was flagged the values become NaN, so a timed-out sweep cannot pass for a valid loss."""
+    epoch = ws.epoch if ws.epoch < 0x80000000 else ws.epoch - 0x100000000
+    bad = ws.buf[:4].view(torch.int32) == epoch
+    return torch.where(bad, torch.full_like(out, float("nan")), out)
+
+
 def _check_inputs(score: torch.Tensor, noiseScore: torch.Tensor):
     # the reference asserts these in TorchScript (:17-18, :111-112, :209-215, :377-382)
     assert score.dim() == 3, "score must be [T, T, nBatch]"
@@ -232,9 +247,15 @@ def _pairs_to_lists(pairs: torch.Tensor, counts: torch.Tensor) -> Intervals:
 # ---------------------------------------------------------------------------
 def _alpha_beta(score: torch.Tensor, noise: torch.Tensor):
     """alpha (forward) and beta (backward) log-sum tables; two independent sweeps."""
-    _, _, alpha, _ = sweep(score, noise, FORWARD, SWEEP_LOGSUM, slot=1)
-    _, _, beta, _ = sweep(score, noise, BACKWARD, SWEEP_LOGSUM, slot=0)
-    return alpha, beta
+    _, _, alpha, wsa = sweep(score, noise, FORWARD, SWEEP_LOGSUM, slot=1)
+    _, _, beta, wsb = sweep(score, noise, BACKWARD, SWEEP_LOGSUM, slot=0)
+    return alpha, beta, (wsa, wsb)
+
+
+def _poison_all(wss, out: torch.Tensor) -> torch.Tensor:
+    for ws in wss:
+        out = _poison_if_flagged(ws, out)
+    return out
 
 
 def _marginals(score, noise, alpha, beta, gscale, want_score: bool, want_noise: bool):
@@ -261,10 +282,10 @@ class _LogZFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, noiseScore):
         s, z = _prep(score), _prep(noiseScore)
-        alpha, beta = _alpha_beta(s, z)
+        alpha, beta, wss = _alpha_beta(s, z)
         ctx.save_for_backward(s, z, alpha, beta)
         ctx.in_dtypes = (score.dtype, noiseScore.dtype)
-        return alpha[-1].clone()  # logZ = v[-1] (:417)
+        return _poison_all(wss, alpha[-1].clone())  # logZ = v[-1] (:417)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -331,11 +352,11 @@ class _LogProbFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, noiseScore, pairs, offsets):
         s, z = _prep(score), _prep(noiseScore)
-        alpha, beta = _alpha_beta(s, z)
+        alpha, beta, wss = _alpha_beta(s, z)
         path = _evalpath_forward(s, z, pairs, offsets)
         ctx.save_for_backward(s, z, alpha, beta, pairs, offsets)
         ctx.in_dtypes = (score.dtype, noiseScore.dtype)
-        return path - alpha[-1]
+        return _poison_all(wss, path - alpha[-1])
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -406,14 +427,13 @@ class NeuralSemiCRFInterval:
         pairs, counts = backtrack(code, forced, direction)
         logz = None
         if with_logz:
-            logz = lse[T - 1 if forward else 0].clone()
+            logz = _poison_if_flagged(ws, lse[T - 1 if forward else 0].clone())
         self._last_ws = ws
         return pairs, counts, logz
 
     def _raise_if_timed_out(self):
         ws = getattr(self, "_last_ws", None)
-        if ws is not None and int(ws.buf[:4].view(torch.int32).item()) != 0:
-            raise _lib.TkbError("semi-CRF sweep: an inter-CTA wait timed out; results are invalid")
+        _raise_if_flagged(ws)
 
     # -- reference surface -------------------------------------------------------------------
     def decode(self, forcedStartPos=None, forward=False) -> Intervals:
@@ -445,8 +465,8 @@ class NeuralSemiCRFInterval:
             # the closed-form marginals are that gradient
             return _LogZFn.apply(self.score, self.noiseScore)
         s, z = _prep_score_for_sweep(self.score), _prep(self.noiseScore)
-        _, _, alpha, _ = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
-        return alpha[-1].clone()
+        _, _, alpha, ws = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
+        return _poison_if_flagged(ws, alpha[-1].clone())
 
     def logProb(self, intervals: Intervals, noBackward=False):
         """evalPath - computeLogZ (reference :587-588)"""
@@ -456,5 +476,5 @@ class NeuralSemiCRFInterval:
         if needs_grad:
             return _LogProbFn.apply(self.score, self.noiseScore, pairs, offsets)
         s, z = _prep(self.score), _prep(self.noiseScore)
-        _, _, alpha, _ = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
-        return _evalpath_forward(s, z, pairs, offsets) - alpha[-1]
+        _, _, alpha, ws = sweep(s, z, FORWARD, SWEEP_LOGSUM, slot=1)
+        return _poison_if_flagged(ws, _evalpath_forward(s, z, pairs, offsets) - alpha[-1])

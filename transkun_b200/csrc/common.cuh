@@ -12,14 +12,6 @@ namespace tkb {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);  // records the error, returns (int)e
 
-// experimental strip design of the sweep (semicrf_sweep_strip.cu), selected with TKB_SWEEP=strip
-namespace strip {
-size_t workspace_bytes(int T, int N);
-int sweep(const float *score, long long pitch, const float *noise, int T, int N, int direction, int flags,
-          void *workspace, uint32_t epoch, uint32_t *out_code, float *out_vit, float *out_lse, void *stream);
-void set_timeline(unsigned long long *buf);
-}  // namespace strip
-
 #define TKB_CUDA(call)                                          \
     do {                                                        \
         cudaError_t _e = (call);                                \
@@ -67,6 +59,34 @@ __device__ __forceinline__ float4 lds128(unsigned saddr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2; each half rounds exactly like the scalar op) ----
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// 16 bytes of shared memory as two packed pairs
+__device__ __forceinline__ void lds128_2(unsigned saddr, unsigned long long &lo, unsigned long long &hi) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
 __device__ __forceinline__ unsigned long long lds64(unsigned saddr) {
     unsigned long long v;
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
@@ -86,6 +106,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Weak L2 load (no L1 allocation).  The mailbox protocol needs no ordering between words -- every 8-byte word carries
+// its own epoch tag -- and consecutive ld.relaxed.gpu loads of one thread were measured to complete one after the other
+// (~80-250 cycles each) instead of overlapping, so look-ahead reads use this and only polls use the relaxed load.
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
