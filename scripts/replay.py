@@ -1,8 +1,6 @@
 """Free-running time of the sweep kernel: a launch that re-uses the previous launch's epoch finds every mailbox word and
 far partial already valid, so nobody waits -- the duration is the slower role's own pace.  CUDA events around the bare
-C-ABI call (outputs preallocated).  With the diagnostics build (TKB_LIBRARY=..._timeline.so) TKB_DBG selects ablations:
-1 = streaming CTAs skip the arithmetic, 2 = skip the score prefetch, 4 = no timeline stamps (always set here).
-usage: python scripts/replay.py [T] [N] [flags]"""
+C-ABI call (outputs preallocated).  usage: python scripts/replay.py [T] [N] [flags]"""
 import ctypes
 import os
 import sys
@@ -56,8 +54,3 @@ for e in range(4, 9):
     torch.cuda.synchronize()
     dep.append(e0.elapsed_time(e1) * 1e3)
 print(f"T={T} N={N} flags={flags}: dependent launch {min(dep):.1f} us (best of 5), replay {timed(8):.1f} us", flush=True)
-if hasattr(L, "tkb_debug_set_flags"):
-    for dbg in (5, 6, 7, 15, 31, 63, 68):
-        L.tkb_debug_set_flags(dbg)
-        print(f"   replay with debug flags {dbg} (1 no arithmetic, 2 no score prefetch, 4 no stamps, 8 no mailbox handshake, 16 no mailbox producers, 32 consumers leave at once, 64 solver CTAs only): {timed(8):.1f} us", flush=True)
-    L.tkb_debug_set_flags(4)

@@ -33,11 +33,11 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_sizes(lib):
     assert lib.tkb_version() == 1
-    # sweep workspace: header + row mailbox (4 replicas * 2 semirings * T * ceil8(N) words) + far partials
-    # ([blocks][2 semirings][ceil8(N)][32 columns][2] words)
+    # sweep workspace: header + row mailbox (2 semirings * T * ceil8(N) words) + far partials
+    # ([groups of 8 tracks][blocks][2 semirings][8][32 columns][2] words)
     def ws(T, N):
-        npad, nb = (N + 7) // 8 * 8, (T + 31) // 32
-        return 256 + 4 * 2 * T * npad * 8 + nb * 2 * npad * 32 * 2 * 8
+        npad, nb, G = (N + 7) // 8 * 8, (T + 31) // 32, (N + 7) // 8
+        return 256 + 2 * T * npad * 8 + G * nb * 2 * 8 * 32 * 2 * 8
     assert lib.tkb_sweep_workspace_bytes(2048, 88) == ws(2048, 88)
     assert lib.tkb_sweep_workspace_bytes(10, 9) == ws(10, 9)
     assert lib.tkb_sweep_workspace_bytes(300, 1200) == ws(300, 1200)

@@ -1,4 +1,4 @@
-// semicrf_sweep.cu -- the semi-Markov dynamic programme as ONE persistent kernel (solver CTAs + streaming CTAs).
+// semicrf_sweep.cu -- the semi-Markov dynamic programme as ONE persistent kernel (solver / helper CTAs).
 //
 // Replaces the TorchScript step loops of the reference
 // (transkun/CRF/NeuralSemiCRFInterval.py:31-51, :124-144, :218-234, :303-327):
@@ -8,45 +8,40 @@
 // read of the score triangle.
 //
 // Mirrored coordinates.  x is the position being solved, y > x a solved one.
-//   BACKWARD: x = begin b, y = end e, S(y,x) = score[e][b]      (sx = P,    sy = T*P)
+//   BACKWARD: x = begin b, y = end e, S(y,x) = score[e][b]      (sx = N,    sy = T*N)
 //   FORWARD : x = T-1-end, y = T-1-begin, S(y,x) = score[T-1-x][T-1-y]
-//                                                               (sx = -T*P, sy = -P)
+//                                                               (sx = -T*N, sy = -N)
 // so one kernel serves viterbiBackward/beta and viterbi/alpha.
 //
-// It is a lower-triangular solve: T strictly sequential steps per track.  The design:
-//   * SOLVER CTAs (one per 4 tracks = 16 bytes of the track-innermost layout) keep the chain inside one SM from
-//     the last position to the first: one warp per track and semiring, lane = column of the current 32-column
-//     block.  A chain step broadcasts the just-finished row with shuffles and pushes it into the current block
-//     (the diagonal tile, on the chain) and into the next ND blocks (off the chain).  The score values come from a
-//     shared-memory ring of "row bands" (32 rows x (ND+1)*32 columns x 16 B).  In the BACKWARD direction with a
-//     16-byte aligned track pitch ONE thread fills a band with ONE TMA tensor copy
-//     (cp.async.bulk.tensor.3d, box {4 tracks, 96 columns, 32 rows}, mbarrier complete_tx): the chain's own SM
-//     does no address generation for it.  (The per-lane cp.async gather of round 1 kept the SM's L1 pipe busy for
-//     ~6000 of the ~7000 cycles of a block and slowed the chain 2x; it remains for FORWARD / unaligned inputs.)
-//     Finished rows leave through a shared-memory ring to one publisher warp per track, which does the global
-//     stores (mailbox, back-pointer codes, tables).
-//   * STREAMING CTAs (all remaining SMs) own the columns round-robin in chunks of two (column x -> CTA
-//     (x/2) mod H) over ALL tracks of the launch, so the bytes a CTA reads of one row are contiguous runs of
-//     2 x N x 4 bytes.  A thread owns (column, 4 tracks): Viterbi max/argmax and log-sum (M,S) accumulators live in
-//     its registers from row T-1 down to the last far row of its column block; nothing is merged across threads.
-//     Rows are consumed in lock-step with the chain in batches of 8: two fetch warps validate the mailbox words of
-//     a batch once per CTA and put the plain values into shared memory; the score rows were prefetched with
-//     cp.async (16 B per thread and row, 3 batches ahead -- they do not depend on the chain).  When a column block's
-//     far field is complete its 32 columns (16 CTAs) publish the "far partial" the solver merges in.
-//   * rows travel solver -> streaming CTAs through a global-memory mailbox of 64-bit words {fp32 value, epoch},
-//     far partials travel back the same way: one relaxed store publishes, one relaxed load observes (no fence, no
-//     flag, no reset; the epoch grows with every launch).
+// It is a lower-triangular solve: T strictly sequential steps per track.  The design keeps that
+// chain inside ONE SM from the first to the last position, and lets every other SM stream the
+// triangle:
+//   * tracks are independent; a GROUP is 8 tracks = one 32-byte sector of the track-innermost layout;
+//   * per group two SOLVER CTAs (4 tracks = 16 bytes each) run the chain: one warp per track and semiring
+//     (the Viterbi and the log-sum chain of a track sit on the same SMSP, their dependent steps interleave),
+//     lane = column of the current 32-column block.  A chain step broadcasts the just-finished row with
+//     shuffles and pushes it into the current block (the diagonal tile, on the chain) and into the next ND
+//     blocks (off the chain); the score values come from a shared-memory ring of "row bands" (32 rows x
+//     (ND+1)*32 columns x 16 B) that four loader warps of the same CTA keep filled with cp.async,
+//     mbarrier-synchronised; finished rows leave through a shared-memory ring to one publisher warp per
+//     track, which does the global stores (mailbox, back-pointer codes, tables);
+//   * per group H HELPER CTAs own the column blocks round-robin and stream everything further than ND
+//     blocks above the diagonal (the bulk of the bytes): 16 warps, each every 16th pair of rows,
+//     cp.async FIFOs, register accumulators, merged once per block and handed to the solvers as a
+//     "far partial";
+//   * rows travel solver -> helpers through a global-memory mailbox of 64-bit words {fp32 value, epoch},
+//     far partials travel helper -> solver the same way: one relaxed store publishes, one relaxed load
+//     observes (no fence, no flag, no reset; the epoch grows with every launch).
 // All CTAs of a launch must be co-resident (cooperative launch).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace tkb {
 
+constexpr int NG = 8;      // tracks per group
 constexpr int NQ = 4;      // tracks per solver CTA
 constexpr int BX = 32;     // columns per block (= lanes of a chain warp)
 #ifndef TKB_ND
@@ -55,39 +50,30 @@ constexpr int BX = 32;     // columns per block (= lanes of a chain warp)
 constexpr int ND = TKB_ND;  // blocks above the diagonal block that the solver pushes itself
 constexpr int NBAND = (ND == 2) ? 4 : 3;  // row bands resident in a solver CTA
 constexpr int BANDCOLS = (ND + 1) * BX;
-constexpr int NW = 16;     // warps per CTA
+#ifndef TKB_NW
+#define TKB_NW 16
+#endif
+constexpr int NW = TKB_NW;  // warps per CTA (helper: NW row slices; solver: chain, loader, publisher warps)
 constexpr int NT = NW * 32;
-constexpr int NCW = NQ;    // chain warps per semiring
-constexpr int NLW = 4;     // loader warps (cp.async path); the first one hosts the TMA thread
-constexpr int PB = 8;      // rows per publish batch = rows per streaming batch
-constexpr int NREP = 4;    // replicas of the row mailbox: streaming CTA h reads replica h % NREP (see publisher warps)
+constexpr int NCW = NQ;    // chain warps
+constexpr int NLW = 4;     // loader warps
+#ifndef TKB_SLOTS
+#define TKB_SLOTS 4
+#endif
+constexpr int SLOTS = TKB_SLOTS;  // helper: per-warp FIFO depth in row PAIRS; SLOTS-1 pairs in flight
+constexpr int PB = 8;      // rows per publish batch
 #ifndef TKB_FARFETCH_BATCH
 #define TKB_FARFETCH_BATCH 3
 #endif
 
-// ---- streaming CTA geometry ----
-constexpr int CW = 2;                  // columns per chunk
-constexpr int NPW = 4;                 // mailbox producer warps: (semiring, half of a batch's rows): the last four warps
-constexpr int NCONSW = NW - NPW;       // consumer warps
-constexpr int NCONS = NCONSW * 32;     // consumer threads
-constexpr int IPT = 2;                 // items (column, 4 tracks) per consumer thread, at most
-constexpr int QB = 4;                  // batches of validated mailbox rows resident (plain floats); a power of two
-#ifndef TKB_QS
-#define TKB_QS 3
-#endif
-constexpr int QS = TKB_QS;             // batches of raw mailbox words in flight (bulk copies)
-constexpr size_t kBarBytes = 256;
-constexpr int NLMAX = 128;             // tracks per launch, at most
-constexpr int MAXSTG = 4;              // score batches in flight, at most
-constexpr size_t kSmemMax = 227 * 1024;
-// streaming CTA shared memory: barriers | qbuf [QB batches][row][semiring][NLP] floats | raw mailbox words | score FIFO
-// [stage][row][NI] 16 bytes
-__host__ __device__ constexpr size_t qbuf_bytes(int nlp) { return (size_t)QB * PB * 2 * nlp * 4; }
-__host__ __device__ constexpr size_t qraw_bytes(int nlp) { return (size_t)NPW * QS * 4 * nlp * 8; }  // [warp][stage][row][NLP]
-__host__ __device__ constexpr size_t fifo_budget(int nlp) { return kSmemMax - kBarBytes - qbuf_bytes(nlp) - qraw_bytes(nlp); }
-static_assert(2 * QB * 8 + NPW * QS * 8 <= kBarBytes, "barrier area");
-static_assert(NREP * PB == 32, "one publisher store instruction writes a batch to every replica");
-
+// helper shared memory: per-warp S FIFO (1 KB per row) | per-warp mailbox-row FIFO (tagged) | untagged copy.
+// After its far field a warp reuses its own (drained) S FIFO for the partial accumulators it hands to the
+// merge: [2 semirings][NG][BX] float2 = 4 KB of its 8 KB.
+constexpr size_t kRingFloatsPerWarp = (size_t)SLOTS * 2 * 2 * 32 * 4;  // [slot][row][col][lane] float4
+constexpr size_t kRingFloats = (size_t)NW * kRingFloatsPerWarp;
+constexpr size_t kQWordsPerWarp = (size_t)SLOTS * 32;    // [slot][row][kind][track] tagged words
+constexpr size_t kQcFloatsPerWarp = (size_t)SLOTS * 32;  // untagged copy, same layout
+constexpr size_t kHelperSmem = kRingFloats * 4 + (size_t)NW * kQWordsPerWarp * 8 + (size_t)NW * kQcFloatsPerWarp * 4;
 // solver shared memory: row bands [NBAND][BX rows][BANDCOLS][NQ tracks] | mbarriers full[NBAND], empty[NBAND]
 constexpr size_t kBandBytes = (size_t)BX * BANDCOLS * NQ * 4;
 // | publish ring [NCW tracks][2 blocks][BX][2 semirings] 8-byte results | mbarriers pub full[NCW][2 blocks][BX/PB]
@@ -95,8 +81,9 @@ constexpr size_t kBandBytes = (size_t)BX * BANDCOLS * NQ * 4;
 constexpr size_t kPubBytes = (size_t)NCW * 2 * BX * 2 * 8;
 constexpr size_t kSolverSmem =
     (size_t)NBAND * kBandBytes + 2 * NBAND * 8 + kPubBytes + NCW * 2 * (BX / PB) * 8 + NCW * 2 * 8;
-constexpr size_t kSweepSmem = kSmemMax;
-static_assert(kSolverSmem <= kSmemMax, "shared memory budget");
+constexpr size_t kSweepSmem = kHelperSmem > kSolverSmem ? kHelperSmem : kSolverSmem;
+static_assert(kRingFloatsPerWarp * 4 >= 2 * NG * BX * 8, "partials must fit the warp's own FIFO");
+static_assert(kSweepSmem <= 227 * 1024, "shared memory budget");
 static_assert(kBandBytes % 128 == 0, "TMA destination alignment");
 
 constexpr size_t kHeaderBytes = 256;  // status word lives here
@@ -105,24 +92,21 @@ struct SweepParams {
     const float *Sbase;    // &S(0,0) in mirrored coordinates
     const float *etabase;  // &skip weight of x = 0
     long long sx, sy, se;  // element strides
-    int T, N, Npad, dir;
-    int n_lo, Nl;          // tracks of this launch
-    int S, H;              // solver CTAs, streaming CTAs
-    int nslots, nitems, NI, nstg;  // streaming geometry (host-computed)
+    int T, N, Npad, G, H, g0, dir;
     unsigned epoch;
-    unsigned long long *mbox;  // [NREP replicas][2 semirings][T][Npad] {value, epoch}
-    unsigned long long *part;  // [nb][2 semirings][Npad][BX][2] {value, epoch}: far partials
+    unsigned long long *mbox;  // [2 semirings][T][Npad] {value, epoch}
+    unsigned long long *part;  // [G][nb][2 semirings][NG][BX][2] {value, epoch}: far partials
     int *status;               // 0, or the epoch of a launch whose inter-CTA wait timed out
     unsigned *code;  // [N][T]
     float *outv;     // [T][N] or null
     float *outl;     // [T][N] or null
-    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][256][8] globaltimer stamps
-    int dbg;                       // diagnostics build only: 1 = streaming CTAs skip the arithmetic, 2 = skip the score prefetch
+    unsigned long long *timeline;  // diagnostics build only (TKB_TIMELINE): [grid][64][4] globaltimer stamps
 };
 
 // Wait until a mailbox word carries this launch's epoch.  A protocol bug (or a non-co-resident grid) must not
-// hang the GPU: after ~4 s the wait gives up, flags the workspace with this launch's epoch and lets the kernel
-// drain with garbage.  BACKOFF_NS > 0 is for waits that are NOT close to a deadline.
+// hang the GPU: after ~4 s the wait gives up, flags the workspace and lets the kernel drain with garbage.
+// BACKOFF_NS > 0 is for waits that are NOT close to a deadline (far rows): hundreds of warps spinning on the few
+// mailbox lines the chain is currently writing slow the chain's own writer down.
 template <int BACKOFF_NS>
 __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w, unsigned epoch, int *status) {
     unsigned long long t0 = globaltimer_ns();
@@ -139,6 +123,9 @@ __device__ __noinline__ unsigned long long poll_slow(const unsigned long long *w
         }
     }
 }
+#ifndef TKB_FAR_BACKOFF_NS
+#define TKB_FAR_BACKOFF_NS 400
+#endif
 __device__ __forceinline__ void publish(unsigned long long *w, float val, unsigned epoch) {
     st_relaxed_u64(w, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(val));
 }
@@ -149,9 +136,6 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // arrival that fires once all cp.async issued so far by this thread have landed (count pre-charged at init)
 __device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar) {
@@ -173,32 +157,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
         : "memory");
     return ok != 0;
 }
-// non-blocking test (no hardware suspend): for waits whose wake-up latency matters
-__device__ __forceinline__ bool mbar_test_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __noinline__ void mbar_spin_slow(unsigned bar, unsigned parity, int *status, unsigned epoch) {
-    unsigned long long t0 = globaltimer_ns();
-    for (;;) {
-        for (int i = 0; i < 4096; ++i)
-            if (mbar_test_wait(bar, parity)) return;
-        if (*(volatile unsigned *)status == epoch) return;
-        if (globaltimer_ns() - t0 > 4000000000ull) {
-            atomicExch(status, (int)epoch);
-            return;
-        }
-    }
-}
 // same watchdog as poll_slow: a protocol bug must drain the kernel, not hang the GPU
 __device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity, int *status, unsigned epoch) {
     unsigned long long t0 = globaltimer_ns();
@@ -215,14 +173,8 @@ __device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity, int *
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, int *status, unsigned epoch) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, status, epoch);
 }
-__device__ __forceinline__ void mbar_spin(unsigned bar, unsigned parity, int *status, unsigned epoch) {
-#ifdef TKB_SPIN
-    for (int i = 0; i < 64; ++i)
-        if (mbar_test_wait(bar, parity)) return;
-    mbar_spin_slow(bar, parity, status, epoch);
-#else
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, status, epoch);
-#endif
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // one band: box {NQ tracks, BANDCOLS columns, BX rows} of the [T][T][N] tensor -> [row][column][track]
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned bar) {
@@ -243,12 +195,17 @@ __device__ __forceinline__ void sts64_nc(unsigned saddr, unsigned lo, unsigned h
 __device__ __forceinline__ void mbar_arrive_nc(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar));
 }
+__device__ __forceinline__ float lds32(unsigned saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
 
 #ifdef TKB_TIMELINE
-// [grid][256 batches / chain blocks][4] stamps
+// [grid][64 owned blocks / 64 chain blocks][4] stamps
 #define TKB_STAMP(idx, slot)                                                                    \
     do {                                                                                        \
-        if (p.timeline && !(p.dbg & 4) && (idx) < 256) p.timeline[((size_t)blockIdx.x * 256 + (idx)) * 8 + (slot)] = globaltimer_ns(); \
+        if (p.timeline && (idx) < 64) p.timeline[((size_t)blockIdx.x * 64 + (idx)) * 4 + (slot)] = globaltimer_ns(); \
     } while (0)
 #else
 #define TKB_STAMP(idx, slot) \
@@ -265,441 +222,282 @@ __device__ __forceinline__ void lse_push(float &M, float &S, float a, float sb) 
 }
 
 // =================================================================================================
-// STREAMING CTA, mailbox producer warp: (semiring `kind`, half `hf` of every batch's 8 rows)
-// =================================================================================================
-// The {value, epoch} words of a batch travel mailbox -> shared memory with bulk copies (cp.async.bulk, one per row, QS
-// batches deep, completion on an mbarrier): no register is waiting for an L2 round trip -- long-latency loads of
-// several batches in flight alias on the six scoreboard slots of a warp, which serialised the register version of
-// this loop at one L2 round trip per batch.  The warp then validates the words in shared memory (they must carry this
-// launch's epoch) and stores the plain floats for the consumers.  While a word is missing, ONE lane sleeps on the row
-// of this half that is solved last and the rows are copied again only then (hundreds of warps re-reading the lines
-// the publishers are writing would slow the writers down).
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-template <int NKIND>
-__device__ __noinline__ void mailbox_producer(const SweepParams &p, int h, int pw, int kind, int hf, int k, int btop,
-                                              int bmin, unsigned qbuf_s, unsigned qraw_s, unsigned qfull_s,
-                                              unsigned qempty_s, unsigned rawfull_s) {
-#ifdef TKB_TIMELINE
-    if (p.dbg & 16) return;
-#endif
-    const int lane = threadIdx.x & 31;
-    const int T = p.T, Nl = p.Nl;
-    const unsigned epoch = p.epoch;
-    const int NLP = (Nl + 3) & ~3;
-    const unsigned qbuf_stride = (unsigned)(PB * NKIND * NLP * 4);
-    const unsigned long long *mb = p.mbox + ((size_t)(h % NREP) * 2 + kind) * T * p.Npad + p.n_lo;
-    const unsigned raw0 = qraw_s + (unsigned)(pw * QS * 4 * NLP * 8);   // [stage][row][NLP] words of this warp
-    const unsigned bar0 = rawfull_s + (unsigned)(pw * QS * 8);
-    const unsigned row_bytes = (unsigned)(((Nl + 1) & ~1) * 8);
-    auto raw_issue = [&](int bb, int stage) {   // rows 4*hf .. 4*hf+3 of batch bb (lanes 0..3 copy one row each)
-        if (bb < bmin) return;
-        const int y0 = bb * PB + 4 * hf;
-        const int nrows = min(4, T - y0);
-        if (nrows <= 0) return;
-        // (the stage was last READ by this warp, before the __syncwarp of the caller: no proxy fence needed for
-        // the write-after-read; ~300 cycles per batch with one)
-        if (lane == 0) mbar_arrive_expect_tx(bar0 + stage * 8, row_bytes * nrows);
-        __syncwarp();
-        if (lane < nrows)
-            bulk_g2s(raw0 + (unsigned)((stage * 4 + lane) * NLP * 8), mb + (size_t)(y0 + lane) * p.Npad, row_bytes,
-                     bar0 + stage * 8);
-    };
-    for (int s = 0; s < QS - 1; ++s) raw_issue(btop - s, s);
-    unsigned ph = 0;   // bit s: parity of the phase stage s completes next
-    int it = 0;
-#ifdef TKB_TIMELINE
-    long long ck[6] = {0, 0, 0, 0, 0, 0};
-    long long c0 = clock64(), c1;
-#define TKB_PK(k) do { c1 = clock64(); ck[k] += c1 - c0; c0 = c1; } while (0)
-#else
-#define TKB_PK(k) do {} while (0)
-#endif
-    for (int b = btop; b >= bmin; --b, ++it) {
-        const int stage = it % QS, buf = it % QB;
-        __syncwarp();  // every lane is done with the stage the next copies overwrite
-        if (threadIdx.x == NCONS) TKB_STAMP(it, 4);
-        TKB_PK(0);
-        raw_issue(b - (QS - 1), (it + QS - 1) % QS);
-        TKB_PK(1);
-        const int y0 = b * PB + 4 * hf;
-        const int nrows = min(4, T - y0);
-#ifdef TKB_TIMELINE
-        if (!(p.dbg & 8))
-#endif
-        if (it >= QB) mbar_spin(qempty_s + buf * 8, ((it / QB) - 1) & 1, p.status, epoch);
-        TKB_PK(2);
-        if (nrows > 0) {
-            mbar_spin(bar0 + stage * 8, (ph >> stage) & 1, p.status, epoch);
-            ph ^= 1u << stage;
-            TKB_PK(3);
-            if (threadIdx.x == NCONS) TKB_STAMP(it, 5);
-            const unsigned st = raw0 + (unsigned)(stage * 4 * NLP * 8);
-            const unsigned dstb = qbuf_s + (unsigned)buf * qbuf_stride;
-            unsigned long long t0 = 0;
-            for (unsigned tries = 0;; ++tries) {
-                bool ok = true;
-                // all loads first (their latencies overlap), then the checks and the stores
-                unsigned long long w[4][4];
-#pragma unroll
-                for (int jn = 0; jn < 4; ++jn) {
-                    const int n = lane + 32 * jn;
-                    // (reading a row of the stage that was not copied is harmless: the value is not used)
-                    if (n < Nl) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) w[jn][r] = lds64(st + (unsigned)((r * NLP + n) * 8));
-                    }
-                }
-#pragma unroll
-                for (int jn = 0; jn < 4; ++jn) {
-                    const int n = lane + 32 * jn;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (n < Nl && r < nrows) {
-                            if ((unsigned)(w[jn][r] >> 32) == epoch)
-                                sts32(dstb + (unsigned)((((4 * hf + r) * NKIND + k) * NLP + n) * 4),
-                                      __uint_as_float((unsigned)w[jn][r]));
-                            else
-                                ok = false;
-                        }
-                }
-                if (__all_sync(kFull, ok)) break;
-                if (threadIdx.x == NCONS) TKB_STAMP(it, 6);
-                // the copy ran ahead of the chain: wait for the last-solved row of this half, then copy it again
-                if (lane == 0) {
-                    const unsigned long long *cw = mb + (size_t)y0 * p.Npad + (h % Nl);
-                    for (int kk = 0; kk < 64 && (unsigned)(ld_relaxed_u64(cw) >> 32) != epoch; ++kk) __nanosleep(100);
-                }
-                bool dead = false;
-                if ((tries & 15) == 15) {   // watchdog
-                    if (t0 == 0) t0 = globaltimer_ns();
-                    dead = *(volatile unsigned *)p.status == epoch || globaltimer_ns() - t0 > 4000000000ull;
-                }
-                if (__any_sync(kFull, dead)) {
-                    if (lane == 0) atomicExch(p.status, (int)epoch);
-                    break;
-                }
-                // the stage's barrier is reused for the repeat: one more phase
-                if (lane == 0) mbar_arrive_expect_tx(bar0 + stage * 8, row_bytes * nrows);
-                __syncwarp();
-                if (lane < nrows)
-                    bulk_g2s(st + (unsigned)(lane * NLP * 8), mb + (size_t)(y0 + lane) * p.Npad, row_bytes, bar0 + stage * 8);
-                mbar_spin(bar0 + stage * 8, (ph >> stage) & 1, p.status, epoch);
-                ph ^= 1u << stage;
-            }
-        }
-        TKB_PK(4);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qfull_s + buf * 8);
-        if (threadIdx.x == NCONS) TKB_STAMP(it, 7);
-        TKB_PK(5);
-    }
-    if (threadIdx.x == NCONS) TKB_STAMP(255, 1);
-#ifdef TKB_TIMELINE
-    if (p.timeline && lane == 0)   // cycle totals: stamp idx 248..253, slots 2..5 = producer warps 0..3
-        for (int kk = 0; kk < 6; ++kk) p.timeline[((size_t)blockIdx.x * 256 + 248 + kk) * 8 + 2 + pw] = (unsigned long long)ck[kk];
-#endif
-}
-
-// =================================================================================================
-// STREAMING CTA: far partials of the owned columns, all tracks of the launch, in lock-step with the chain
+// HELPER: far partial of the owned column blocks
 // =================================================================================================
 template <int DIR, int ALIGN, int MODE>
-__device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char *smem_raw, int h) {
+__device__ __forceinline__ void helper_role(const SweepParams &p, unsigned char *smem_raw, int g, int h) {
     constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
     constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
-    constexpr int NKIND = (DO_V ? 1 : 0) + (DO_L ? 1 : 0);
-    const int T = p.T, Nl = p.Nl;
+    constexpr bool A16 = ALIGN == 16;
+    constexpr int D = SLOTS - 1;
+
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    unsigned long long *qring = reinterpret_cast<unsigned long long *>(ring + kRingFloats);
+    float *qcomp = reinterpret_cast<float *>(qring + (size_t)NW * kQWordsPerWarp);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, N = p.N;
     const int nb = (T + BX - 1) / BX;
+    const int n0 = g * NG;
     const unsigned epoch = p.epoch;
-    const int NLP = (Nl + 3) & ~3;
-    const int nvec = NLP >> 2;
-    const int t = threadIdx.x;
+    unsigned long long *mboxV = p.mbox;
+    unsigned long long *mboxL = p.mbox + (size_t)T * p.Npad;
 
-    const unsigned bar_s = smem_u32(smem_raw);
-    const unsigned qbuf_s = bar_s + (unsigned)kBarBytes;              // [QB][row][semiring slot][NLP] floats
-    const unsigned qraw_s = qbuf_s + (unsigned)qbuf_bytes(NLP);       // [producer warp][stage][row][NLP] tagged words
-    const unsigned fifo_s = qraw_s + (unsigned)qraw_bytes(NLP);       // [stage][row][NI] float4
+    // far-field mapping: lane -> (column pair, track quad)
+    const int cpair = lane >> 1, quad = lane & 1;
+    const int nq = n0 + quad * 4;
+    const int nvalid = min(max(N - nq, 0), 4);
+    float *my_ring = ring + (size_t)warp * kRingFloatsPerWarp + lane * 4;  // + slot*256 (+128 for column 1)
+    unsigned long long *my_q = qring + (size_t)warp * kQWordsPerWarp;
+    float *my_qc = qcomp + (size_t)warp * kQcFloatsPerWarp;
+    float2 *my_partV = reinterpret_cast<float2 *>(ring + (size_t)warp * kRingFloatsPerWarp);  // [NG][BX]
+    float2 *my_partL = my_partV + NG * BX;
+    // merge mapping: warp -> (semiring, track), lane -> column
+    const int sn = warp & 7;
+    const bool s_is_lse = warp >= 8;
+    const long long row_step = (long long)NW * p.sy;
+    const long long q_step = (long long)NW * p.Npad;
 
-    // batches b = btop .. bmin (8 rows each, descending); the CTA's smallest column is 2h
-    if (2 * h >= T) return;
-    const int J0 = (2 * h) / BX;
-    if (J0 > nb - ND - 2) return;                     // no far field at all
-    const int btop = (T - 1) / PB;
-    const int bmin = (BX / PB) * (J0 + ND + 1);       // batch of the first far row of column block J0
-
-    const int warp = t >> 5, lane = t & 31;
-    const unsigned qfull_s = bar_s, qempty_s = bar_s + QB * 8, rawfull_s = bar_s + 2 * QB * 8;
-    if (t == 0) {
-        for (int s = 0; s < QB; ++s) {
-            mbar_init(qfull_s + s * 8, 2 * NKIND);   // the batch's producer warps arrive
-            mbar_init(qempty_s + s * 8, NCONSW);
-        }
-        for (int s = 0; s < NPW * QS; ++s) mbar_init(rawfull_s + s * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const unsigned qbuf_stride = (unsigned)(PB * NKIND * NLP * 4);
-
-    if (warp >= NCONSW) {
-        const int pw = warp - NCONSW;            // 0..3 -> (semiring, half of the batch's rows)
-        const int kind = pw >> 1;                // 0 Viterbi, 1 log-sum
-        if (!(kind ? DO_L : DO_V)) return;
-        const int k = (DO_V && DO_L) ? kind : 0;  // semiring slot inside a qbuf row
-        mailbox_producer<NKIND>(p, h, pw, kind, pw & 1, k, btop, bmin, qbuf_s, qraw_s, qfull_s, qempty_s, rawfull_s);
-        return;
-    }
-
-    // ---- items: (column, 4 tracks) ----------------------------------------------------------------------------
-    bool valid[IPT];
-    int ix[IPT], iv[IPT], ibend[IPT];
-    const float *isrc[IPT];   // &S(0, x) + track offset; row y adds y * sy
-    int nbytes[IPT];
-    float vmax[IPT][4], lM[IPT][4], lS[IPT][4];
-    int vsel[IPT][4];
+    int owned_idx = 0;
+    for (int J = nb - ND - 2 - h; J >= 0; J -= p.H, ++owned_idx) {
+        const int x0 = J * BX;
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 0);
+        float vmax[2][4], lM[2][4], lS[2][4];
+        int vsel[2][4];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const int item = t + i * NCONS;
-        const int m = item / (CW * nvec), rem = item - m * (CW * nvec);
-        const int c = rem / nvec, v = rem - c * nvec;
-        const int x = CW * (h + m * p.H) + c;
-        const int J = x / BX;
-        valid[i] = item < p.nitems && x < T && J <= nb - ND - 2;
-        ix[i] = x;
-        iv[i] = v;
-        ibend[i] = (BX / PB) * (J + ND + 1);
-        nbytes[i] = min(4, Nl - 4 * v) * 4;
-        isrc[i] = valid[i] ? p.Sbase + (long long)x * p.sx + p.n_lo + 4 * v : p.Sbase;
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            vmax[i][q] = -INFINITY;
-            vsel[i][q] = -1;
-            lM[i][q] = -FLT_MAX;
-            lS[i][q] = 0.0f;
-        }
-    }
-    const int nstg = p.nstg;
-    const unsigned stage_bytes = (unsigned)PB * p.NI * 16u;
-    // prefetch of batch bb: 8 rows x 16 bytes per item, into stage (btop - bb) % nstg
-    int istage = 0;   // stage of the next batch to prefetch: (btop - bb) % nstg without the division
-    // running source pointers: row 8*bb of the next batch to prefetch (one pointer step per batch, one per row)
-    const long long bstep = (long long)PB * p.sy;
-    const float *nsrc[IPT];
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) nsrc[i] = isrc[i] + (long long)btop * bstep;
-    const unsigned rstride_i = (unsigned)p.NI * 16u;
-    auto issue = [&](int bb) {
-        const unsigned st = fifo_s + (unsigned)istage * stage_bytes;
-        istage = istage + 1 == nstg ? 0 : istage + 1;
-#ifdef TKB_TIMELINE
-        if (p.dbg & 2) { cp_async_commit(); return; }
-#endif
-        if (bb >= bmin) {
-#pragma unroll
-            for (int i = 0; i < IPT; ++i) {
-                if (valid[i] && bb >= ibend[i]) {
-                    unsigned dst = st + (unsigned)(t + i * NCONS) * 16u;
-                    const float *src = nsrc[i];
-                    if (bb * PB + PB <= T && ALIGN == 16) {   // the common case: eight rows, 16-byte copies
-#pragma unroll
-                        for (int r = 0; r < PB; ++r) {
-                            cp_async16_s(dst, src, nbytes[i]);
-                            dst += rstride_i;
-                            src += p.sy;
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < PB; ++r) {
-                            if (bb * PB + r < T) {
-                                if (ALIGN == 16) {
-                                    cp_async16_s(dst, src, nbytes[i]);
-                                } else {
-                                    for (int q = 0; q * 4 < nbytes[i]; ++q) cp_async4_s(dst + q * 4, src + q, 4);
-                                }
-                            }
-                            dst += rstride_i;
-                            src += p.sy;
-                        }
-                    }
-                }
-                nsrc[i] -= bstep;
+            for (int q = 0; q < 4; ++q) {
+                vmax[j][q] = -INFINITY;
+                vsel[j][q] = -1;
+                lM[j][q] = -FLT_MAX;
+                lS[j][q] = 0.0f;
             }
-        }
-        cp_async_commit();
-    };
-    for (int s = 0; s < nstg - 1; ++s) issue(btop - s);
-
-    int cstage = 0;
-#ifdef TKB_TIMELINE
-    long long ck[6] = {0, 0, 0, 0, 0, 0};
-    long long c0 = clock64(), c1;
-#define TKB_CK(k) do { c1 = clock64(); ck[k] += c1 - c0; c0 = c1; } while (0)
-#else
-#define TKB_CK(k) do {} while (0)
-#endif
-    for (int b = btop, it = 0; b >= bmin; --b, ++it) {
-#ifdef TKB_TIMELINE
-        if (p.dbg & 32) break;
-#endif
-        if (t == 0) TKB_STAMP(it, 0);
-        TKB_CK(0);
-        issue(b - (nstg - 1));
-        TKB_CK(1);
-        if (nstg == 4) cp_async_wait<3>();
-        else if (nstg == 3) cp_async_wait<2>();
-        else cp_async_wait<1>();
-        TKB_CK(2);
-        const int buf = it & (QB - 1);
-#ifdef TKB_TIMELINE
-        if (!(p.dbg & 8))
-#endif
-        mbar_spin(qfull_s + buf * 8, (it / QB) & 1, p.status, epoch);
-        TKB_CK(3);
-        if (t == 0) TKB_STAMP(it, 1);
-        const unsigned st = fifo_s + (unsigned)cstage * stage_bytes;
-        cstage = cstage + 1 == nstg ? 0 : cstage + 1;
-        const unsigned qb = qbuf_s + (unsigned)buf * qbuf_stride;
-        const int y0 = b * PB;
-#ifdef TKB_TIMELINE
-        const bool skip_math = (p.dbg & 1) != 0;
-#else
-        constexpr bool skip_math = false;
-#endif
+        const int R = T - (x0 + (ND + 1) * BX);   // rows y = T-1 .. x0+(ND+1)*BX, taken in adjacent pairs (R >= 1)
+        const int npairs = (R + 1) >> 1;          // pair pr = rows (T-1-2pr, T-2-2pr); the last may be half
+        const int mypairs = npairs > warp ? (npairs - warp + NW - 1) / NW : 0;
+        {
+            // running source pointers of the next pair to issue (all 32 columns are valid here); pairs past
+            // the end are issued with src-size 0 (no global access), so the loop body has no branches
+            const float *sp0 = p.Sbase;
+            if (nvalid > 0)
+                sp0 = p.Sbase + (long long)(x0 + 2 * cpair) * p.sx + (long long)(T - 1 - 2 * warp) * p.sy + nq;
+            const long long sstep = nvalid > 0 ? 2 * row_step : 0;
+            const long long scol = nvalid > 0 ? p.sx : 0;
+            const long long srow = nvalid > 0 ? p.sy : 0;
+            // mailbox fetch: lane = row*8 + kind*4 + track pair (lanes 0-15); tag check: lane = row*16 + kind*8 + track
+            const int f_row = lane >> 3, f_kind = (lane >> 2) & 1;
+            const bool qfetch = lane < 16 && (f_kind ? DO_L : DO_V);
+            const unsigned long long *qp =
+                (f_kind ? mboxL : mboxV) + (long long)(T - 1 - 2 * warp - f_row) * p.Npad + n0 + 2 * (lane & 3);
+            const int c_row = lane >> 4, c_kind = (lane >> 3) & 1;
+            const bool c_need = (c_kind ? DO_L : DO_V) && (n0 + (lane & 7)) < N;  // padding tracks are never published
+            const unsigned long long *cq = (c_kind ? mboxL : mboxV) + n0 + (lane & 7);  // + y * Npad
+            const float c_absent = c_kind ? -FLT_MAX : -INFINITY;  // q of a row that does not exist
+            const int nbytes = nvalid * 4;
+            const unsigned ring_s = smem_u32(my_ring);  // + slot*2048 + row*1024 + col*512
+            const unsigned q_s = smem_u32(my_q);        // + slot*256: tagged words [row][kind][track]
+            const unsigned qc_s = smem_u32(my_qc);      // + slot*128: untagged values [row][kind][track]
+            int ti = 0;  // next pair to issue
+            auto issue = [&]() {
+                const int live = ti < mypairs;
+                const int liveB = live && (2 * (warp + ti * NW) + 1 < R);
+                const unsigned so = (unsigned)(ti % SLOTS) * 2048u;
+                if (A16) {
+                    cp_async16_s(ring_s + so, sp0, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 512, sp0 + scol, live ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 1024, sp0 - srow, liveB ? nbytes : 0);
+                    cp_async16_s(ring_s + so + 1536, sp0 - srow + scol, liveB ? nbytes : 0);
+                } else if (ALIGN == 8) {
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            if (valid[i] && b >= ibend[i] && !(skip_math && b != ibend[i])) {
-                const unsigned src = st + (unsigned)(t + i * NCONS) * 16u;
-                const unsigned qsrc = qb + (unsigned)(iv[i] * 16);
-                const unsigned rstride = (unsigned)p.NI * 16u, qstride = (unsigned)(NKIND * NLP * 4);
-                const unsigned long long kL2 = pack2(kLog2e, kLog2e);
-                // FULL = all eight rows of the batch exist (every batch but a ragged first one): no per-row branch, so
-                // the shared-memory loads of a half-batch are issued together and their latencies overlap
-                auto rows = [&](auto full_tag) {
-                    constexpr bool FULL = decltype(full_tag)::value;
-#pragma unroll
-                    for (int half = 1; half >= 0; --half) {   // rows 7..4, then 3..0 (descending y: tie order)
-                        if (FULL || y0 + 4 * half < T) {
-                            unsigned long long x01[4], x23[4];   // log-sum candidates of four rows, packed by track pair
-#pragma unroll
-                            for (int rr = 3; rr >= 0; --rr) {
-                                const int r = 4 * half + rr, y = y0 + r;
-                                if (FULL || y < T) {
-                                    unsigned long long s01, s23;
-                                    lds128_2(src + (unsigned)r * rstride, s01, s23);
-                                    if (DO_V) {
-                                        unsigned long long q01, q23;
-                                        lds128_2(qsrc + (unsigned)r * qstride, q01, q23);
-                                        float xv[4];
-                                        unpack2(add2(q01, s01), xv[0], xv[1]);   // one fp32 add per candidate, as the reference
-                                        unpack2(add2(q23, s23), xv[2], xv[3]);
-#pragma unroll
-                                        for (int q = 0; q < 4; ++q) {
-                                            const bool tk = (DIR == TKB_BACKWARD) ? (xv[q] >= vmax[i][q]) : (xv[q] > vmax[i][q]);
-                                            vmax[i][q] = tk ? xv[q] : vmax[i][q];
-                                            vsel[i][q] = tk ? y : vsel[i][q];
-                                        }
-                                    }
-                                    if (DO_L) {
-                                        unsigned long long q01, q23;
-                                        lds128_2(qsrc + (unsigned)r * qstride + (unsigned)((NKIND - 1) * NLP * 4), q01, q23);
-                                        x01[rr] = fma2(s01, kL2, q01);
-                                        x23[rr] = fma2(s23, kL2, q23);
-                                    }
-                                } else if (DO_L) {
-                                    x01[rr] = x23[rr] = pack2(-FLT_MAX, -FLT_MAX);
-                                }
-                            }
-                            if (DO_L) {
-                                float xs[4][4];
-#pragma unroll
-                                for (int rr = 0; rr < 4; ++rr) {
-                                    unpack2(x01[rr], xs[rr][0], xs[rr][1]);
-                                    unpack2(x23[rr], xs[rr][2], xs[rr][3]);
-                                }
-                                float Mn[4], sc[4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float m = fmaxf(fmaxf(xs[0][q], xs[1][q]), fmaxf(xs[2][q], xs[3][q]));
-                                    Mn[q] = fmaxf(lM[i][q], m);
-                                    sc[q] = ex2f(lM[i][q] - Mn[q]);
-                                    lM[i][q] = Mn[q];
-                                }
-                                const unsigned long long nM01 = pack2(-Mn[0], -Mn[1]), nM23 = pack2(-Mn[2], -Mn[3]);
-                                unsigned long long a01 = mul2(pack2(lS[i][0], lS[i][1]), pack2(sc[0], sc[1]));
-                                unsigned long long a23 = mul2(pack2(lS[i][2], lS[i][3]), pack2(sc[2], sc[3]));
-#pragma unroll
-                                for (int rr = 0; rr < 4; ++rr) {
-                                    float d0, d1, d2, d3;
-                                    unpack2(add2(x01[rr], nM01), d0, d1);
-                                    unpack2(add2(x23[rr], nM23), d2, d3);
-                                    a01 = add2(a01, pack2(ex2f(d0), ex2f(d1)));
-                                    a23 = add2(a23, pack2(ex2f(d2), ex2f(d3)));
-                                }
-                                unpack2(a01, lS[i][0], lS[i][1]);
-                                unpack2(a23, lS[i][2], lS[i][3]);
-                            }
-                        }
+                    for (int q = 0; q < 4; q += 2) {
+                        const int qq = q < nvalid ? q : 0;
+                        const int nA = (live && q < nvalid) ? 8 : 0, nB = (liveB && q < nvalid) ? 8 : 0;
+                        cp_async8_s(ring_s + so + q * 4, sp0 + qq, nA);
+                        cp_async8_s(ring_s + so + 512 + q * 4, sp0 + scol + qq, nA);
+                        cp_async8_s(ring_s + so + 1024 + q * 4, sp0 - srow + qq, nB);
+                        cp_async8_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
                     }
-                };
-                if (y0 + PB <= T) rows(std::true_type{});
-                else rows(std::false_type{});
-                if (b == ibend[i]) {
-                    // the far field of this column is complete: hand it to the solver of each of my tracks
-                    const int J = ix[i] / BX, cx = ix[i] - J * BX;
-                    unsigned long long *dst =
-                        p.part + (((size_t)J * 2) * p.Npad + p.n_lo + 4 * iv[i]) * (BX * 2) + 2 * cx;
+                } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (q * 4 < nbytes[i]) {
-                            if (DO_V) {
-                                publish(dst + (size_t)q * (BX * 2), vmax[i][q], epoch);
-                                publish(dst + (size_t)q * (BX * 2) + 1, __int_as_float(vsel[i][q]), epoch);
-                            }
-                            if (DO_L) {
-                                publish(dst + ((size_t)p.Npad + q) * (BX * 2), lM[i][q], epoch);
-                                publish(dst + ((size_t)p.Npad + q) * (BX * 2) + 1, lS[i][q], epoch);
-                            }
-                        }
+                        const int qq = q < nvalid ? q : 0;
+                        const int nA = (live && q < nvalid) ? 4 : 0, nB = (liveB && q < nvalid) ? 4 : 0;
+                        cp_async4_s(ring_s + so + q * 4, sp0 + qq, nA);
+                        cp_async4_s(ring_s + so + 512 + q * 4, sp0 + scol + qq, nA);
+                        cp_async4_s(ring_s + so + 1024 + q * 4, sp0 - srow + qq, nB);
+                        cp_async4_s(ring_s + so + 1536 + q * 4, sp0 - srow + scol + qq, nB);
                     }
+                }
+                if (qfetch) cp_async16_s(q_s + (so >> 3) + lane * 16, qp, (f_row ? liveB : live) ? 16 : 0);
+                sp0 -= sstep;
+                qp -= 2 * q_step;
+                ++ti;
+            };
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                issue();
+                cp_async_commit();
+            }
+            int yA = T - 1 - 2 * warp;
+            // one pair of rows: wait for S and the mailbox words, validate the tags, distribute q, Viterbi update,
+            // and (log-sum) stage x = S*log2e + q for the pair flush
+            auto do_pair = [&](int t, float (&xlA)[2][4], float (&xlB)[2][4]) {
+                issue();
+                cp_async_commit();
+                cp_async_wait<D>();
+                __syncwarp();
+                const unsigned so = (unsigned)(t % SLOTS);
+                const bool hasB = 2 * (warp + t * NW) + 1 < R;
+                unsigned long long word = lds64(q_s + so * 256 + lane * 8);
+                const bool need = c_need && (c_row == 0 || hasB);
+                const bool ok = !need || (unsigned)(word >> 32) == epoch;
+                if (!__all_sync(kFull, ok)) {  // row not published when prefetched: poll it now
+                    if (!ok) {
+                        const unsigned long long *w = cq + (long long)(yA - c_row) * p.Npad;
+                        word = (yA < x0 + (ND + 3) * BX) ? poll_slow<0>(w, epoch, p.status)
+                                                         : poll_slow<TKB_FAR_BACKOFF_NS>(w, epoch, p.status);
+                    }
+                }
+                const float qrow = (c_row && !hasB) ? c_absent : __uint_as_float((unsigned)word);
+                sts32(qc_s + so * 128 + lane * 4, qrow);
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {  // row A = yA, then row B = yA - 1 (descending y: tie order)
+                    float4 qv4, ql4;
+                    if (DO_V) qv4 = lds128(qc_s + so * 128 + rr * 64 + quad * 16);
+                    if (DO_L) ql4 = lds128(qc_s + so * 128 + rr * 64 + 32 + quad * 16);
+                    const float4 a0 = lds128(ring_s + so * 2048 + rr * 1024);
+                    const float4 a1 = lds128(ring_s + so * 2048 + rr * 1024 + 512);
+                    const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
+                    const float ql[4] = {ql4.x, ql4.y, ql4.z, ql4.w};
+                    const float av[2][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}};
+                    const int y = yA - rr;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (DO_V) {
+                                const float xv = qv[q] + av[j][q];
+                                const bool tk = (DIR == TKB_BACKWARD) ? (xv >= vmax[j][q]) : (xv > vmax[j][q]);
+                                vmax[j][q] = tk ? xv : vmax[j][q];
+                                vsel[j][q] = tk ? y : vsel[j][q];
+                            }
+                            if (DO_L) (rr ? xlB : xlA)[j][q] = fmaf(av[j][q], kLog2e, ql[q]);
+                        }
+                }
+                yA -= 2 * NW;
+            };
+            for (int t = 0; t < mypairs; ++t) {  // one max/rescale per pair of rows
+                float xl[2][2][4];
+                do_pair(t, xl[0], xl[1]);
+                if (DO_L) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float m = fmaxf(xl[0][j][q], xl[1][j][q]);
+                            const float Mn = fmaxf(lM[j][q], m);
+                            float acc = lS[j][q] * ex2f(lM[j][q] - Mn);
+                            acc += ex2f(xl[0][j][q] - Mn);
+                            acc += ex2f(xl[1][j][q] - Mn);
+                            lS[j][q] = acc;
+                            lM[j][q] = Mn;
+                        }
                 }
             }
         }
-        TKB_CK(4);
-        if (t == 0) TKB_STAMP(it, 2);
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 1);
+        // ---- hand the 16 partials to the merge mapping (via this warp's drained FIFO) --------
+        cp_async_wait_all();
         __syncwarp();
-        if (lane == 0) mbar_arrive(qempty_s + buf * 8);
-        TKB_CK(5);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int o = (quad * 4 + q) * BX + 2 * cpair + j;
+                if (DO_V) my_partV[o] = make_float2(vmax[j][q], __int_as_float(vsel[j][q]));
+                if (DO_L) my_partL[o] = make_float2(lM[j][q], lS[j][q]);
+            }
+        __syncthreads();
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 2);
+        const int c = lane;
+        unsigned long long *dst =
+            p.part + ((((size_t)g * nb + J) * 2 + (s_is_lse ? 1 : 0)) * NG + sn) * (BX * 2) + 2 * c;
+        if (warp >= 16) {
+            // (more than 16 row slices: the extra warps have nothing to merge)
+        } else if (!s_is_lse && DO_V) {
+            // branch-free NW-way merge: the maximum, then among the partials that attain it the row the
+            // reference's candidate order prefers (BACKWARD: smallest y, FORWARD: largest y).  Empty partials
+            // are (-inf, -1); (unsigned)-1 is the largest unsigned, so they never win the min.
+            float pv[NW];
+            int ps[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float2 e = reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[sn * BX + c];
+                pv[w] = e.x;
+                ps[w] = __float_as_int(e.y);
+            }
+            float best = pv[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) best = fmaxf(best, pv[w]);
+            int bsel;
+            if (DIR == TKB_BACKWARD) {
+                unsigned m = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) m = min(m, pv[w] == best ? (unsigned)ps[w] : 0xffffffffu);
+                bsel = (int)m;
+            } else {
+                int m = -1;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) m = max(m, pv[w] == best ? ps[w] : -1);
+                bsel = m;
+            }
+            publish(dst, best, epoch);
+            publish(dst + 1, __int_as_float(bsel), epoch);
+        } else if (s_is_lse && DO_L) {
+            float M = -FLT_MAX, S = 0.0f;
+            float m[NW], s[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float2 e =
+                    reinterpret_cast<const float2 *>(ring + (size_t)w * kRingFloatsPerWarp)[(NG + sn) * BX + c];
+                m[w] = e.x;
+                s[w] = e.y;
+                M = fmaxf(M, e.x);
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) S += s[w] * ex2f(m[w] - M);
+            publish(dst, M, epoch);
+            publish(dst + 1, S, epoch);
+        }
+        if (threadIdx.x == 0) TKB_STAMP(owned_idx, 3);
+        __syncthreads();  // the partials live in the FIFOs the next owned block refills
     }
-    cp_async_wait_all();
-#ifdef TKB_TIMELINE
-    if (p.timeline && (t & 31) == 0 && t < 64) {   // cycle totals of warps 0 and 1: stamp slots 248..253
-        for (int k = 0; k < 6; ++k) p.timeline[((size_t)blockIdx.x * 256 + 248 + k) * 8 + (t >> 5)] = (unsigned long long)ck[k];
-    }
-#endif
 }
 
 // One chain warp: track n0 + tr, lane = column of the current block, semirings CV / CL.  When a launch computes
 // both, each track has two chain warps (one per semiring) on the same SMSP: their dependent chains interleave.
 struct ChainCtx {
     unsigned full_s, empty_s, pub_s, pubfull_s, pubempty_s;
-    int n0, tr;
+    int g, qd, n0, tr;
 };
 template <int DIR, bool CV, bool CL>
 __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *smem_raw, const ChainCtx &cx) {
     constexpr bool DO_V = CV, DO_L = CL;
     const int lane = threadIdx.x & 31;
-    const int T = p.T;
+    const int T = p.T, N = p.N;
     const int nb = (T + BX - 1) / BX;
     const unsigned epoch = p.epoch;
     const unsigned full_s = cx.full_s, empty_s = cx.empty_s, pub_s = cx.pub_s, pubfull_s = cx.pubfull_s,
                    pubempty_s = cx.pubempty_s;
-    const int n0 = cx.n0, tr = cx.tr;
+    const int g = cx.g, qd = cx.qd, n0 = cx.n0, tr = cx.tr;
+    (void)N;
     // ---------------- chain warp: track n, lane = column ---------------------------------------------
     const int n = n0 + tr;
     const int c = lane;
+    const int ptrk = qd * NQ + tr;  // track inside the group
+    (void)epoch;
     // accumulators: [0] the block on the chain, [d] the block d below it
     float best[ND + 1], lM[ND + 1], lS[ND + 1];
     int bsel[ND + 1];
@@ -728,14 +526,14 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
     const unsigned long long *fsrc = nullptr;
     auto far_fetch = [&](int jn) {
         if (jn < 0 || jn > nb - ND - 2) return;
-        fsrc = p.part + (((size_t)jn * 2) * p.Npad + n) * (BX * 2) + 2 * c;
+        fsrc = p.part + ((((size_t)g * nb + jn) * 2) * NG + ptrk) * (BX * 2) + 2 * c;
         if (DO_V) {
-            fw[0] = ld_cg_u64(fsrc);
-            fw[1] = ld_cg_u64(fsrc + 1);
+            fw[0] = ld_relaxed_u64(fsrc);
+            fw[1] = ld_relaxed_u64(fsrc + 1);
         }
         if (DO_L) {
-            fw[2] = ld_cg_u64(fsrc + (size_t)p.Npad * BX * 2);
-            fw[3] = ld_cg_u64(fsrc + (size_t)p.Npad * BX * 2 + 1);
+            fw[2] = ld_relaxed_u64(fsrc + (size_t)NG * BX * 2);
+            fw[3] = ld_relaxed_u64(fsrc + (size_t)NG * BX * 2 + 1);
         }
     };
     const float *bands = reinterpret_cast<const float *>(smem_raw);
@@ -754,39 +552,12 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
             sp2 = fmaxf(d2, 0.0f) + lg2f(1.0f + ex2f(-fabsf(d2)));  // softplus(d)*log2e
             eta2 = s_eta * kLog2e;
         }
-        if (threadIdx.x == 0) TKB_STAMP(it, 0);
-        if (lane == 0) TKB_STAMP(128 + it, (DO_V ? 0 : 4) + tr);
-        // ---- far partial of this block (rows of blocks > j+ND), written by the streaming CTAs --------------
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 0);
+        // ---- far partial of this block (rows of blocks > j+ND), written by the owning helper -------------
         if (j <= nb - ND - 2) {
-            {
-                // all words of the partial in one round trip per attempt
-                const unsigned long long *srcL = fsrc + (size_t)p.Npad * BX * 2;
-                unsigned long long t0 = 0;
-                for (unsigned tries = 0;; ++tries) {
-                    bool ok = true;
-                    if (DO_V) ok &= (unsigned)(fw[0] >> 32) == epoch && (unsigned)(fw[1] >> 32) == epoch;
-                    if (DO_L) ok &= (unsigned)(fw[2] >> 32) == epoch && (unsigned)(fw[3] >> 32) == epoch;
-                    if (ok) break;
-                    if ((tries & 63) == 63) {  // watchdog, off the fast path
-                        if (t0 == 0) t0 = globaltimer_ns();
-                        if (*(volatile unsigned *)p.status == epoch) break;
-                        if (globaltimer_ns() - t0 > 4000000000ull) {
-                            atomicExch(p.status, (int)epoch);
-                            break;
-                        }
-                    }
-                    __nanosleep(40);
-                    if (DO_V) {
-                        fw[0] = ld_relaxed_u64(fsrc);
-                        fw[1] = ld_relaxed_u64(fsrc + 1);
-                    }
-                    if (DO_L) {
-                        fw[2] = ld_relaxed_u64(srcL);
-                        fw[3] = ld_relaxed_u64(srcL + 1);
-                    }
-                }
-            }
             if (DO_V) {
+                if ((unsigned)(fw[0] >> 32) != epoch) fw[0] = poll_slow<0>(fsrc, epoch, p.status);
+                if ((unsigned)(fw[1] >> 32) != epoch) fw[1] = poll_slow<0>(fsrc + 1, epoch, p.status);
                 const float fv = __uint_as_float((unsigned)fw[0]);
                 const int fs = (int)(unsigned)fw[1];
                 // far rows are larger y than anything accumulated so far: BACKWARD prefers the smaller y on ties
@@ -794,9 +565,14 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
                 bsel[0] = tk ? fs : bsel[0];
                 best[0] = fmaxf(best[0], fv);
             }
-            if (DO_L) lse_push(lM[0], lS[0], __uint_as_float((unsigned)fw[2]), __uint_as_float((unsigned)fw[3]));
+            if (DO_L) {
+                const unsigned long long *srcL = fsrc + (size_t)NG * BX * 2;
+                if ((unsigned)(fw[2] >> 32) != epoch) fw[2] = poll_slow<0>(srcL, epoch, p.status);
+                if ((unsigned)(fw[3] >> 32) != epoch) fw[3] = poll_slow<0>(srcL + 1, epoch, p.status);
+                lse_push(lM[0], lS[0], __uint_as_float((unsigned)fw[2]), __uint_as_float((unsigned)fw[3]));
+            }
         }
-        if (threadIdx.x == 0) TKB_STAMP(it, 1);
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 1);
         // ---- the skip out of the top column into row 32(j+1): candidate 0 of the reference, wins every tie ----
         if (j < nb - 1) {
             if (DO_V) {
@@ -818,7 +594,6 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
         }
         // ---- wait for the row band ------------------------------------------------------------------
         mbar_wait(full_s + slot * 8, (it / NBAND) & 1, p.status, epoch);
-        if (threadIdx.x == 0) TKB_STAMP(it, 3);
         // my column in the diagonal tile is band column ND*32 + c; in the tile d blocks below, (ND-d)*32 + c
         const float *colp = bands + (size_t)slot * (kBandBytes / 4) + c * NQ + tr;
         // log-sum: the skip x -> x+1 folded into the coefficient of the row right above my column
@@ -896,7 +671,7 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
                 publish_batch(e8);
             }
         }
-        if (threadIdx.x == 0) TKB_STAMP(it, 2);
+        if (lane == 0 && tr == 0) TKB_STAMP(it, 2);
         // ---- next block: release the band, shift the accumulators ------------------------------------------
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_s + slot * 8);
@@ -912,7 +687,6 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
         lM[ND] = -FLT_MAX;
         lS[ND] = 0.0f;
     }
-    if (threadIdx.x == 0) TKB_STAMP(255, 0);
 }
 
 // =================================================================================================
@@ -920,15 +694,20 @@ __device__ __forceinline__ void chain_warp(const SweepParams &p, unsigned char *
 // =================================================================================================
 template <int DIR, int ALIGN, int MODE>
 __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensorMap *map, unsigned char *smem_raw,
-                                            int s) {
+                                            int g, int qd) {
     constexpr bool DO_V = (MODE & TKB_SWEEP_VITERBI) != 0;
     constexpr bool DO_L = (MODE & TKB_SWEEP_LOGSUM) != 0;
+    // BACKWARD with a 16-byte aligned track pitch: ONE thread fills a band with ONE TMA tensor copy
+    // (cp.async.bulk.tensor.3d, box {4 tracks, 96 columns, 32 rows}); the per-lane cp.async gather of round 1 touched
+    // 32 different 128-byte lines per instruction and kept this SM's L1 pipe busy ~6000 of the ~7000 cycles of a block,
+    // slowing the chain it shares the SM with (profiles/r02_sweep_experiments.txt: 243 -> 131 cycles per column in
+    // the chain microbenchmark under load)
     constexpr bool USE_TMA = (DIR == TKB_BACKWARD) && (ALIGN == 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, N = p.N;
     const int nb = (T + BX - 1) / BX;
-    const int n0 = p.n_lo + s * NQ;                        // first track of this solver
-    const int nvalid = min(max(p.n_lo + p.Nl - n0, 0), NQ);  // chain warps with a real track
+    const int n0 = g * NG + qd * NQ;           // first track of this solver
+    const int nvalid = min(max(N - n0, 0), NQ);  // chain warps with a real track
     const unsigned epoch = p.epoch;
     const unsigned band_s = smem_u32(smem_raw);
     const unsigned full_s = band_s + (unsigned)(NBAND * kBandBytes);  // + slot*8
@@ -938,25 +717,25 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
     const unsigned pubempty_s = pubfull_s + NCW * 2 * (BX / PB) * 8;  // [tr][block parity]
 
     if (threadIdx.x == 0) {
-        for (int sl = 0; sl < NBAND; ++sl) {
-            mbar_init(full_s + sl * 8, USE_TMA ? 1 : NLW * 32);
-            mbar_init(empty_s + sl * 8, nvalid * ((DO_V && DO_L) ? 2 : 1));
+        for (int s = 0; s < NBAND; ++s) {
+            mbar_init(full_s + s * 8, USE_TMA ? 1 : NLW * 32);
+            mbar_init(empty_s + s * 8, nvalid * ((DO_V && DO_L) ? 2 : 1));
         }
-        for (int sl = 0; sl < NCW * 2 * (BX / PB); ++sl)
-            mbar_init(pubfull_s + sl * 8, PB * ((DO_V && DO_L) ? 2 : 1));  // the batch's lanes arrive
-        for (int sl = 0; sl < NCW * 2; ++sl) mbar_init(pubempty_s + sl * 8, 1);
+        for (int s = 0; s < NCW * 2 * (BX / PB); ++s) mbar_init(pubfull_s + s * 8, PB * ((DO_V && DO_L) ? 2 : 1));  // the batch's lanes arrive
+        for (int s = 0; s < NCW * 2; ++s) mbar_init(pubempty_s + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (nvalid == 0) return;
 
     if (warp >= NCW && warp < NCW + NLW) {
-        // ---------------- band producer ----------------------------------------------------------------------
+        // ---------------- loader warps: keep the ring of row bands filled ----------------------------
         // band of row block j: rows y = 32j .. 32j+31, columns x = 32(j-ND) .. 32j+31, this solver's NQ tracks;
-        // chunk (e, cc) -> band + (e*BANDCOLS + cc)*16.
+        // chunk (e, cc) -> band + (e*BANDCOLS + cc)*16.  Chunks above the diagonal, left of column 0 or below
+        // row T-1 are never read and not fetched.
         if (USE_TMA) {
-            // one thread, one tensor copy per band; cells outside the tensor (x < 0, y >= T, track >= N) arrive as
-            // zeros and are never read, like the cells above the diagonal
+            // cells outside the tensor (x < 0, y >= T, track >= N) arrive as zeros and are never read, like the cells
+            // above the diagonal
             if (warp != NCW || lane != 0) return;
             for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
                 const int slot = it % NBAND;
@@ -964,11 +743,8 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
                 mbar_arrive_expect_tx(full_s + slot * 8, (unsigned)kBandBytes);
                 tma_load_3d(band_s + (unsigned)(slot * kBandBytes), map, n0, (j - ND) * BX, j * BX, full_s + slot * 8);
             }
-            TKB_STAMP(255, 2);
             return;
         }
-        // per-lane cp.async gather.  Chunks above the diagonal, left of column 0 or below row T-1 are never read
-        // and not fetched.
         const int lt = threadIdx.x - NCW * 32;
         const int nbytes = nvalid * 4;
         for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
@@ -1002,12 +778,7 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
         const int tr = warp - (NCW + NLW);
         if (tr >= nvalid) return;
         const int n = n0 + tr;
-        // The mailbox is replicated NREP times and the streaming CTAs read "their" replica: every 128-byte mailbox
-        // line is wanted by all of them at the same moment, and an L2 slice hands out one line to ~100 requesters per
-        // microsecond (measured: 126 readers of one replica cost 1.3 us per batch of 8 rows, more than the arithmetic).
-        // One store instruction writes all replicas: lane -> (replica lane / 8, row lane % 8 of the batch).
-        const int rep = lane >> 3, lr = lane & (PB - 1);
-        unsigned long long *mV = p.mbox + ((size_t)rep * 2) * T * p.Npad + n, *mL = mV + (size_t)T * p.Npad;
+        unsigned long long *mV = p.mbox + n, *mL = p.mbox + (size_t)T * p.Npad + n;
         const int bmax_top = (T - (nb - 1) * BX - 1) / PB;  // last batch index of the ragged top block
         for (int j = nb - 1, it = 0; j >= 0; --j, ++it) {
             const int x0 = j * BX;
@@ -1016,32 +787,28 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
                 // batches the ragged top block skips never arrive: their barriers are one phase behind
                 const unsigned npast = (unsigned)(it >> 1) - (((it & 1) == 0 && it > 0 && e8 > bmax_top) ? 1u : 0u);
                 mbar_wait(pubfull_s + (unsigned)(((tr * 2 + (it & 1)) * (BX / PB) + e8) * 8), npast & 1, p.status, epoch);
-                const int c = e8 * PB + lr, x = x0 + c;
-                if (rep < NREP && x < T) {
+                const int c = e8 * PB + lane, x = x0 + c;
+                if (lane < PB && x < T) {
                     const int pos = (DIR == TKB_BACKWARD) ? x : T - 1 - x;
                     const unsigned src = pub_s + (unsigned)((((tr * 2 + (it & 1)) * BX + c) * 2) * 8);
                     if (DO_V) {
                         const unsigned long long w = lds64(src);
                         const float qfin = __uint_as_float((unsigned)w);
                         publish(mV + (size_t)x * p.Npad, qfin, epoch);
-                        if (rep == 0) {
-                            p.code[(size_t)n * T + pos] = (unsigned)(w >> 32);
-                            if (p.outv) p.outv[(size_t)pos * N + n] = qfin;
-                        }
+                        p.code[(size_t)n * T + pos] = (unsigned)(w >> 32);
+                        if (p.outv) p.outv[(size_t)pos * N + n] = qfin;
                     }
                     if (DO_L) {
                         const unsigned long long w = lds64(src + 8);
                         const float v2 = __uint_as_float((unsigned)w) + lg2f(__uint_as_float((unsigned)(w >> 32)));
                         publish(mL + (size_t)x * p.Npad, v2, epoch);
-                        if (rep == 0 && p.outl) p.outl[(size_t)pos * N + n] = v2 * kLn2;
+                        if (p.outl) p.outl[(size_t)pos * N + n] = v2 * kLn2;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pubempty_s + (tr * 2 + (it & 1)) * 8);
-            if (lane == 0) TKB_STAMP(64 + it, tr);
         }
-        if (tr == 0 && lane == 0) TKB_STAMP(255, 1);
         return;
     }
     // ---------------- chain warps ------------------------------------------------------------------------
@@ -1051,6 +818,8 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
     cx.pub_s = pub_s;
     cx.pubfull_s = pubfull_s;
     cx.pubempty_s = pubempty_s;
+    cx.g = g;
+    cx.qd = qd;
     cx.n0 = n0;
     if (DO_V && DO_L) {  // split: Viterbi chains on warps 0..NCW-1, log-sum chains on the last NCW warps
         if (warp < NCW) {
@@ -1069,10 +838,12 @@ __device__ __forceinline__ void solver_role(const SweepParams &p, const CUtensor
 template <int DIR, int ALIGN, int MODE>
 __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ CUtensorMap map, const SweepParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    if ((int)blockIdx.x < p.S)
-        solver_role<DIR, ALIGN, MODE>(p, &map, smem_raw, (int)blockIdx.x);
+    const int per = 2 + p.H;
+    const int g = p.g0 + (int)blockIdx.x / per, role = (int)blockIdx.x % per;
+    if (role < 2)
+        solver_role<DIR, ALIGN, MODE>(p, &map, smem_raw, g, role);
     else
-        helper_role<DIR, ALIGN, MODE>(p, smem_raw, (int)blockIdx.x - p.S);
+        helper_role<DIR, ALIGN, MODE>(p, smem_raw, g, role - 2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1117,7 +888,6 @@ static int launch_align(int align, int mode, const SweepParams &p, const CUtenso
 }
 
 static unsigned long long *g_timeline = nullptr;  // diagnostics build only
-extern int g_dbg_flags;
 static int num_sms() {
     static int sms[kMaxDevices] = {};
     int dev = 0;
@@ -1126,12 +896,12 @@ static int num_sms() {
     return sms[dev];
 }
 static size_t mailbox_bytes(int T, int N) {
-    const size_t npad = (size_t)((N + 7) / 8) * 8;
-    return (size_t)NREP * 2 * (size_t)T * npad * sizeof(unsigned long long);
+    const size_t npad = (size_t)((N + NG - 1) / NG) * NG;
+    return 2 * (size_t)T * npad * sizeof(unsigned long long);
 }
 static size_t partial_bytes(int T, int N) {
-    const size_t npad = (size_t)((N + 7) / 8) * 8, nb = (size_t)((T + BX - 1) / BX);
-    return nb * 2 * npad * BX * 2 * sizeof(unsigned long long);
+    const size_t G = (size_t)((N + NG - 1) / NG), nb = (size_t)((T + BX - 1) / BX);
+    return G * nb * 2 * NG * BX * 2 * sizeof(unsigned long long);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -1149,8 +919,6 @@ static EncodeTiledFn encode_tiled() {
     }
     return fn;
 }
-
-int g_dbg_flags = 0;
 
 }  // namespace tkb
 
@@ -1181,15 +949,15 @@ extern "C" int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, cons
         return TKB_EINVAL;
     }
     const int sms = num_sms();
-    if (sms < 2) {
+    if (sms < 3) {
         set_error("tkb_semicrf_sweep: no CUDA device");
         return TKB_ENODEV;
     }
     SweepParams p;
-    memset(&p, 0, sizeof(p));
     p.T = T;
     p.N = N;
-    p.Npad = (N + 7) / 8 * 8;
+    p.G = (N + NG - 1) / NG;
+    p.Npad = p.G * NG;
     p.dir = direction;
     p.epoch = epoch;
     p.status = reinterpret_cast<int *>(workspace);
@@ -1200,7 +968,6 @@ extern "C" int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, cons
     p.outv = out_vit;
     p.outl = out_lse;
     p.timeline = g_timeline;
-    p.dbg = g_dbg_flags;
     if (direction == TKB_BACKWARD) {
         p.Sbase = score;
         p.sx = pitch;
@@ -1218,7 +985,6 @@ extern "C" int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, cons
     // the track pitch, not N, decides the copy width: a padded score tensor (pitch % 4 == 0) takes the 16-byte path
     const int align = (pitch % 4 == 0 && (addr & 15) == 0) ? 16 : ((pitch % 2 == 0 && (addr & 7) == 0) ? 8 : 4);
     const int nb = (T + BX - 1) / BX;
-
     // TMA descriptor of the score tensor for the solver's band copies (BACKWARD, 16-byte path)
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -1241,44 +1007,17 @@ extern "C" int tkb_semicrf_sweep_pitched(const float *score, int64_t pitch, cons
             return TKB_EINVAL;
         }
     }
-
-    // Launch geometry.  One launch takes Nl <= 128 tracks: S = ceil(Nl/4) solver CTAs and H = SMs - S streaming
-    // CTAs; the streaming CTAs own the columns that have a far field in chunks of two, round-robin.  The tracks are
-    // split over more launches until a streaming CTA's items (column, 4 tracks) fit its threads and its FIFO.
-    const int far_cols = nb - ND - 1 > 0 ? ((nb - ND - 1) * BX < T ? (nb - ND - 1) * BX : T) : 0;
-    const int chunks = (far_cols + CW - 1) / CW;
-    int launches = (N + NLMAX - 1) / NLMAX;
-    int Nl = 0, S = 0, H = 0, nslots = 0, nitems = 0, NI = 8, nstg = 2;
-    for (;; ++launches) {
-        Nl = ((N + launches - 1) / launches + 3) / 4 * 4;
-        if (Nl > NLMAX) continue;
-        S = (Nl + NQ - 1) / NQ;
-        if (S > sms - 1 && chunks > 0) continue;
-        H = sms - S;
-        if (H > chunks) H = chunks;
-        if (H < 0) H = 0;
-        nslots = H > 0 ? (chunks + H - 1) / H : 0;
-        nitems = nslots * CW * (Nl / 4);
-        NI = nitems > 8 ? (nitems + 7) / 8 * 8 : 8;
-        nstg = (int)(fifo_budget(Nl) / ((size_t)PB * NI * 16));
-        if (nstg > MAXSTG) nstg = MAXSTG;
-        if ((nitems <= NCONS * IPT && nstg >= 2) || Nl <= 4) break;
-    }
-    if (nitems > NCONS * IPT || nstg < 2) {
-        set_error("tkb_semicrf_sweep: T=%d is too long for the streaming CTAs of this device", T);
-        return TKB_ELAUNCH;
-    }
-    p.nslots = nslots;
-    p.nitems = nitems;
-    p.NI = NI;
-    p.nstg = nstg;
-    for (int n_lo = 0; n_lo < N; n_lo += Nl) {
-        p.n_lo = n_lo;
-        p.Nl = (N - n_lo) < Nl ? (N - n_lo) : Nl;
-        p.S = (p.Nl + NQ - 1) / NQ;
-        p.H = (g_dbg_flags & 64) ? 0 : H;   // diagnostics: solver CTAs only (replay launches)
-        p.nitems = nslots * CW * ((p.Nl + 3) / 4);
-        const int grid = p.S + p.H;
+    const int hmax = nb - ND - 1 > 1 ? nb - ND - 1 : 1;  // column blocks that have a far field at all
+    // groups are independent pipelines; split them over launches if there are more groups than SMs / 3
+    const int gmax = sms / 3;
+    for (int g0 = 0; g0 < p.G; g0 += gmax) {
+        const int gcount = (p.G - g0) < gmax ? (p.G - g0) : gmax;
+        int H = sms / gcount - 2;
+        if (H > hmax) H = hmax;
+        if (H < 1) H = 1;
+        p.g0 = g0;
+        p.H = H;
+        const int grid = gcount * (2 + H);
         const int rc = direction == TKB_BACKWARD ? launch_align<TKB_BACKWARD>(align, flags, p, map, grid, stream)
                                                  : launch_align<TKB_FORWARD>(align, flags, p, map, grid, stream);
         if (rc != 0) return rc;
@@ -1299,4 +1038,3 @@ extern "C" int tkb_sweep_status(const void *workspace, int *status_host, void *s
 
 // diagnostics build only (compile with -DTKB_TIMELINE): device buffer of [grid][64][4] globaltimer stamps
 extern "C" void tkb_debug_set_timeline(unsigned long long *buf) { g_timeline = buf; }
-extern "C" void tkb_debug_set_flags(int flags) { tkb::g_dbg_flags = flags; }
