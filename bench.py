@@ -15,9 +15,10 @@ e2e      : same metric through the public API from HOST inputs (NeuralSemiCRFInt
            intervals + logZ, and the construction of the Python interval lists, all inside the timed region.
 roofline : dominant kernel (sweep) algorithmic bytes 4*N*T(T+1)/2 per launch / its CUDA-event duration,
            against MEASURED_PEAKS.json's HBM copy bandwidth; traffic = DRAM bytes of the committed ncu capture.
-cpu_baseline / --impl reference : the reference is pure Python/PyTorch and cannot travel to the GPU box,
-           so the CPU arm is the C/OpenMP oracle port (oracle/, checked against the reference's golden
-           outputs) on all host cores.
+cpu_baseline / --impl reference : the reference's OWN PyTorch-CPU path -- the unmodified package installed under
+           baseline/_ref (baseline/ref_loader.py): NeuralSemiCRFInterval(score, noise).computeLogZ(noBackward=True) +
+           .decode() on all host cores (kind "reference").  Only if baseline/_ref is absent does it fall back to the
+           C/OpenMP oracle port (kind "port", ~16x faster than the reference on the same CPU).
 Multi-GPU: tracks shard with no data-path collective (weak scaling: every rank owns its own 88 tracks); the only
            exchange is the all-gather of the packed intervals: copy-engine pushes into symmetric NVLink peer memory on a
            side stream, overlapped with the next step's sweep (transkun_b200.sharded.PushGather; NCCL all-gather
@@ -53,7 +54,18 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tsweep", action="store_true", help="add a T sweep 256..4096 (config 5) to the JSON line")
     return ap.parse_args()
+
+
+def workload_config(T, n_local, n_total, world):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": f"semi-CRF logZ + Viterbi decode on score[T,T,N] fp32 randn (seed 1234 + rank), T={T}, "
+                        f"N={n_local} tracks per GPU",
+            "T": T, "tracks_per_gpu": n_local, "tracks_total": n_total, "parallelism": f"track-sharded x{world}",
+            "l2": "score tensor 1.48 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
+            "timing": "ours: CUDA events on the launching stream, barrier+synchronize both sides, max over ranks; "
+                      "reference arm: perf_counter around K full passes on the host"}
 
 
 def peak_hbm():
@@ -81,6 +93,51 @@ def ncu_traffic(T, N):
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (kind "port")
 # --------------------------------------------------------------------------------------------
+def reference_available():
+    from baseline import ref_loader
+    return ref_loader.available()
+
+
+def time_reference(T, N, steps, warmup, budget_s=240.0):
+    """The unmodified reference on the host cores: computeLogZ(noBackward=True) + decode() per step.  If K+W full
+    passes would not fit the budget, a step is the same pass over the first n tracks (tracks are independent, so
+    cells/s is the per-track rate; the sample is stated)."""
+    import torch
+    from golden_util import make_inputs
+    from baseline import ref_loader
+    RefCRF = ref_loader.reference_crf()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
+    score, noise = make_inputs("randn", T, N, 1234)
+    score_t, noise_t = torch.from_numpy(score), torch.from_numpy(noise)
+
+    def one(s, z):
+        with torch.no_grad():
+            crf = RefCRF(s, z)
+            logz = crf.computeLogZ(noBackward=True)
+            dec = crf.decode()
+        return logz, dec
+
+    t0 = time.perf_counter()
+    one(score_t, noise_t)          # TorchScript profiling run 1 (also the size probe)
+    t_probe = time.perf_counter() - t0
+    n_used = N
+    if t_probe * (steps + warmup) > budget_s:
+        n_used = max(4, int(N * budget_s / (t_probe * (steps + warmup))) // 4 * 4)
+        score_t, noise_t = score_t[:, :, :n_used].contiguous(), noise_t[:, :n_used].contiguous()
+    for _ in range(max(warmup, 2) - (1 if n_used == N else 0)):
+        one(score_t, noise_t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one(score_t, noise_t)
+    sec = (time.perf_counter() - t0) / steps
+    sample = (f"{steps} timed full passes of T={T} N={N}" if n_used == N else
+              f"{steps} timed passes of T={T} over the first {n_used} of {N} tracks (full passes would exceed {budget_s:.0f} s)")
+    return {"value": float(T) * T * n_used / sec, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": sample + ": unmodified reference (baseline/_ref) NeuralSemiCRFInterval.computeLogZ(noBackward=True) "
+                               f"+ .decode(), torch {torch.__version__} CPU, {cores} threads"}, sec
+
+
 def cpu_pass(oracle_mod, score, noise):
     o = oracle_mod.SemiCRFOracle(score, noise)
     logz = o.computeLogZ()           # reference computeLogZ(noBackward=True)
@@ -88,46 +145,43 @@ def cpu_pass(oracle_mod, score, noise):
     return logz, counts
 
 
-def time_cpu(T, N, steps, warmup, budget_s=60.0):
+def time_port(T, N, steps, warmup, budget_s=60.0):
     from golden_util import make_inputs
     from oracle import semicrf_oracle
     semicrf_oracle.build()
     score, noise = make_inputs("randn", T, N, 1234)
     semicrf_oracle.lib().tko_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     cores = semicrf_oracle.lib().tko_max_threads()
-    times = []
-    t_begin = time.perf_counter()
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
+    for _ in range(warmup):
         cpu_pass(semicrf_oracle, score, noise)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
-            break
-    sec = statistics.median(times)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(semicrf_oracle, score, noise)
+    sec = (time.perf_counter() - t0) / steps
     return {"value": T * T * N / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(times)} timed full passes of T={T} N={N} (logZ forward + Viterbi backward + backtrack), "
-                      f"C/OpenMP oracle port, median"}, sec, len(times)
+            "sample": f"{steps} timed full passes of T={T} N={N} (logZ forward + Viterbi backward + backtrack), "
+                      f"C/OpenMP oracle port"}, sec
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps = min(args.steps, 8)
-    warm = min(args.warmup, 2)
-    base, sec, done = time_cpu(args.T, args.tracks, steps, warm, budget_s=150.0)
+    if reference_available():
+        base, sec = time_reference(args.T, args.tracks, args.steps, args.warmup)
+    else:
+        base, sec = time_port(args.T, args.tracks, args.steps, args.warmup)
+    n_total = args.tracks * world if args.scaling == "weak" else args.tracks
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": done, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"semi-CRF logZ+Viterbi decode, T={args.T}, N={args.tracks} fp32 randn seed 1234",
-                   "note": "reference is pure PyTorch and cannot run on the GPU box; CPU arm = C/OpenMP oracle port "
-                           "pinned to the reference's golden outputs"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.T, args.tracks, n_total, world),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "notes": "CPU arm: runs on rank 0's host cores only, whatever --gpus says",
     }
     print(json.dumps(line), flush=True)
 
@@ -215,7 +269,8 @@ def run_ours(args):
     # symmetric memory on a side stream, overlapped with the next step's sweep (transkun_b200.sharded.PushGather);
     # fallback: one NCCL all-gather per step on the compute stream.
     push = None
-    if world > 1 and args.scaling == "weak" and os.environ.get("TKB_GATHER", "push") == "push":
+    # (needs every rank to own the same number of tracks: 88 splits evenly over 2, 4 and 8 GPUs)
+    if world > 1 and n_total % world == 0 and os.environ.get("TKB_GATHER", "push") == "push":
         try:
             push = PushGather(n_local, 2 + 4 * T, dev)
         except Exception as exc:  # no symmetric memory / P2P: NCCL path
@@ -306,41 +361,97 @@ def run_ours(args):
         d2h_bytes = n_local * 4 + n_local * maxc * 8 + logz_h.numel() * 4
     torch.cuda.synchronize(dev)
     e2e_sec = (time.perf_counter() - tw0) / e2e_steps
+    # where an e2e step goes (untimed extra pass, a synchronisation between the phases)
+    bd = {}
+    with torch.no_grad():
+        torch.cuda.synchronize(dev)
+        t_a = time.perf_counter()
+        crf = NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev)
+        torch.cuda.synchronize(dev)
+        t_b = time.perf_counter()
+        pairs_d, counts_d, logz_d = crf.decode_packed(None, False, with_logz=True)
+        torch.cuda.synchronize(dev)
+        t_c = time.perf_counter()
+        counts_h = counts_d.cpu()
+        pairs_h = pairs_d[:, : int(counts_h.max())].cpu()
+        logz_d.cpu()
+        t_d = time.perf_counter()
+        from transkun_b200.CRF.NeuralSemiCRFInterval import _pairs_to_lists
+        _pairs_to_lists(pairs_d, counts_d)
+        t_e = time.perf_counter()
+        bd = {"h2d_ms": (t_b - t_a) * 1e3, "gpu_ms": (t_c - t_b) * 1e3, "d2h_ms": (t_d - t_c) * 1e3,
+              "host_lists_ms": (t_e - t_d) * 1e3 - (t_d - t_c) * 1e3,
+              "note": "h2d = pinned staircase upload of the lower triangle (PCIe); host_lists = building the reference's "
+                      "List[List[Tuple[int,int]]] result (~1.6e5 Python tuples), which the reference's decode() also returns"}
+        del pairs_h
     if world > 1:
         tmax = torch.tensor([e2e_sec], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_sec = float(tmax.item())
     h2d_bytes = NeuralSemiCRFInterval.lowerTriangleUploadBytes(T, n_local) + noise_pin.numel() * 4
 
+    # ---- other shapes of the same kernel (device-generated inputs; CUDA events) -------------------------------
+    def time_shape(Ts, Ns, pad_to=None, reps=10):
+        P = pad_to or Ns
+        buf = torch.randn((Ts, Ts, P), device=dev)
+        sc = buf[:, :, :Ns]
+        nz = torch.randn((Ts - 1, Ns), device=dev)
+        for _ in range(3):
+            sweep(sc, nz, BACKWARD, SWEEP_VITERBI | SWEEP_LOGSUM)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            sweep(sc, nz, BACKWARD, SWEEP_VITERBI | SWEEP_LOGSUM)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        gbs = 4.0 * Ns * Ts * (Ts + 1) / 2.0 / us / 1e3
+        del buf, sc, nz
+        return {"T": Ts, "N": Ns, "track_pitch": P, "sweep_us": us, "GBps": gbs, "cells_per_s": float(Ts) * Ts * Ns / us * 1e6}
+
+    shapes = None
+    if world == 1:
+        del score, noise
+        torch.cuda.empty_cache()
+        shapes = [time_shape(691, 90, pad_to=92), time_shape(1024, 88)]
+        if args.tsweep:
+            shapes += [time_shape(t_, 88, reps=5) for t_ in (256, 512, 2048, 4096)]
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         alg_bytes = 4.0 * n_local * T * (T + 1) / 2.0
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
         traffic = ncu_traffic(T, n_local)
+        for sh in shapes or []:
+            sh["frac_of_hbm_peak"] = sh["GBps"] / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"semi-CRF logZ+Viterbi decode (one fused sweep + device backtrack), T={T}, "
-                                   f"N={n_local} tracks/GPU fp32 randn seed 1234",
-                       "T": T, "tracks_per_gpu": n_local, "tracks_total": n_total, "parallelism": f"track-sharded x{world}",
-                       "exchange": ("none" if world == 1 else ("copy-engine pushes into symmetric memory, overlapped with the "
-                                    "next sweep" if push is not None else "NCCL all-gather per step")),
-                       "l2": "score tensor 1.48 GB per GPU >> 126 MB L2: inputs larger than L2, no flush needed",
-                       "timing": "CUDA events on the launching stream, barrier+synchronize both sides, max over ranks"},
+            "config": workload_config(T, n_local, n_total, world),
+            "exchange": ("none" if world == 1 else ("copy-engine pushes into symmetric memory, overlapped with the "
+                         "next sweep" if push is not None else "NCCL all-gather per step")),
             "e2e": {"value": cells_per_step / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3, "breakdown": bd,
                     "api": "NeuralSemiCRFInterval.fromHost(score, noise, device).decodeWithLogZ() from pinned host tensors "
-                           "(uploads the lower-triangle staircase of score, the part the semi-CRF reads)"},
+                           "(uploads the lower-triangle staircase of score, the part the semi-CRF reads); returns the "
+                           "reference's Python interval lists + logZ"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "tkb::sweep_kernel<BACKWARD, A16, VITERBI|LOGSUM>",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sweep_ms, "peak_source": peak_src},
+            "other_shapes": shapes,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            base, _, _ = time_cpu(T, n_local, 3, 1, budget_s=45.0)
-            line["cpu_baseline"] = base
+            if reference_available():
+                base, _ = time_reference(T, n_local, 3, 2, budget_s=30.0)
+                port, _ = time_port(T, n_local, 3, 1)
+                line["cpu_baseline"] = base
+                line["cpu_baseline_port"] = port
+            else:
+                base, _ = time_port(T, n_local, 3, 1)
+                line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

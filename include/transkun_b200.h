@@ -180,6 +180,17 @@ int tkb_sip_score_pitched(const float *q, const float *k, const float *diag, int
                           float *out_score, int64_t pitch, void *stream);
 
 /*
+ * Same contraction with an explicit scale instead of 1/sqrt(D):
+ *     out[e][b][n] = (sum_d q[n][e][d] * k[n][b][d]) * scale * |e-b|  +  [e==b] * diag[n][e]
+ * This is how the host gets fp32-grade products out of the TF32 tensor cores (the reference's inference path,
+ * transcribe.py, never enables TF32): q and k are split into a TF32-exact high part and a residual, and the kernel
+ * is called once on the concatenation [q_hi, q_hi, q_lo] x [k_hi, k_lo, k_hi] (D' = 3 D) with scale = 1/sqrt(D)
+ * ("3xTF32"; transkun_b200/LayersTransformer.py).
+ */
+int tkb_sip_score_scaled(const float *q, const float *k, const float *diag, int n_tracks, int T, int D, float scale,
+                         float *out_score, int64_t pitch, void *stream);
+
+/*
  * STFT / log-mel frontend.  Replaces Util.py:104-113 (Spectrum.forward) and :156-167
  * (MelSpectrum.forward with log=True): for every frame, audio channel and window
  *     X = rfft(frame * window, norm="ortho");  P = |X|^2;  (to_mono: mean over channels)

@@ -78,3 +78,21 @@ def test_kernel_full_segment_shape_vs_oracle():
 
 
 import math  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lead", [(), (2,), (3, 2), (2, 1, 2)])
+def test_leading_shapes_follow_the_reference(lead):
+    """The reference accepts any leading shape [..., nFrame, W]; toMono averages the dim right before nFrame whenever
+    the input has one (Util.py:158-161, keepdim=True): 2-D frames stay un-averaged, 3-D frames [C, nFrame, W] become
+    [1, nFrame, nMel, nWin]."""
+    from transkun_b200.Util import MelSpectrum
+    torch.manual_seed(len(lead))
+    m = MelSpectrum(256, f_min=30, f_max=8000, n_mels=24, fs=44100, nExtraWins=2, log=True, toMono=True).cuda().eval()
+    frames = torch.randn(*lead, 9, 256)
+    with torch.no_grad():
+        out = m(frames.cuda())
+    wins = m.spectrogramExtractor.windows().detach().cpu().numpy()
+    ref = logmel(frames.numpy(), wins, m.freq2mels.cpu().numpy(), 1e-5, True)
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=2e-5)

@@ -40,7 +40,37 @@ def test_kernel_matches_reference_module(path):
         S, b = m(torch.from_numpy(z["ctx"]).cuda())
     assert S.shape == z["S"].shape and b.shape == z["b"].shape and not b.any()
     got, want = _lower(S.cpu().numpy()), _lower(z["S"])
-    assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
+    # default = the reference's inference regime (allow_tf32 unset): 3xTF32, fp32-grade products
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    assert not np.triu(S.cpu().numpy()[:, :, 0, 0], 1).any(), "cells above the diagonal are defined (zero)"
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True  # the reference's --allow_tf32 training regime: one TF32 pass
+    try:
+        with torch.no_grad():
+            S1, _ = m(torch.from_numpy(z["ctx"]).cuda())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert np.abs(_lower(S1.cpu().numpy()) - want).max() <= 2e-3 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NT,T,D", [(8, 128, 256), (90, 257, 256), (5, 97, 64)])
+def test_kernel_precise_mode_is_fp32_grade(NT, T, D):
+    """3xTF32 (operands split into a TF32-exact part and a residual, contracted as [hi,hi,lo] x [hi,lo,hi]) against a
+    float64 evaluation of the reference formula: error at the level of fp32 accumulation, three orders of magnitude
+    below the one-pass TF32 kernel."""
+    from transkun_b200.LayersTransformer import sip_score
+    g = torch.Generator().manual_seed(NT + T)
+    q, k, diag = torch.randn(NT, T, D, generator=g), torch.randn(NT, T, D, generator=g), torch.randn(NT, T, generator=g)
+    t = torch.arange(T, dtype=torch.float64)
+    want = (torch.einsum("ned,nbd->neb", q.double(), k.double()) / (D ** 0.5)) * (t[:, None] - t[None, :]).abs()
+    want = (want + torch.diag_embed(diag.double())).permute(1, 2, 0)
+    tri = torch.tril(torch.ones(T, T, dtype=torch.bool))
+    scale = want[tri].abs().max().item()
+    err_p = (sip_score(q.cuda(), k.cuda(), diag.cuda(), precise=True).cpu().double() - want)[tri].abs().max().item()
+    err_1 = (sip_score(q.cuda(), k.cuda(), diag.cuda(), precise=False).cpu().double() - want)[tri].abs().max().item()
+    assert err_p <= 3e-6 * scale, (err_p, scale)
+    assert err_1 <= 2e-3 * scale and err_1 > 10 * err_p
 
 
 @pytest.mark.gpu

@@ -45,22 +45,61 @@ def test_entry_reports_missing_reference():
 
 
 def test_install_rebinds_the_real_reference_modules():
-    """With the real reference importable (this container only), install() makes ModelTransformer construct OUR
-    CRF class and, on request, OUR scorer class."""
+    """With the real reference importable (baseline/_ref), install() makes ModelTransformer construct OUR CRF class,
+    OUR scorer class and OUR frontend class; TKB_PATCH_*=0 keeps the reference's torch modules."""
     import pytest
-    if not os.path.isdir("/root/reference/transkun"):
-        pytest.skip("reference checkout not present")
+    sys.path.insert(0, ROOT)
+    from baseline import ref_loader
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref (the installed reference) is not present")
     code = textwrap.dedent("""
-        import sys, types
-        sys.path.insert(0, "/root/reference")
-        for m in ("pretty_midi", "mir_eval", "mir_eval.transcription", "mir_eval.transcription_velocity"):
-            sys.modules[m] = types.ModuleType(m)   # not installed here; unused on this path (SURVEY.md section 8c)
+        import sys
+        sys.path.insert(0, %r)
+        from baseline import ref_loader
+        ref_loader.import_reference()
         from transkun_b200.transcribe import install
-        install(patch_scorer=True)
+        install()
         import transkun.ModelTransformer as MT
-        print(MT.CRF.NeuralSemiCRFInterval.__module__, MT.ScaledInnerProductIntervalScorer.__module__)
-    """)
+        print(MT.CRF.NeuralSemiCRFInterval.__module__, MT.ScaledInnerProductIntervalScorer.__module__, MT.MelSpectrum.__module__)
+    """ % ROOT)
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT),
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert out.stdout.split() == ["transkun_b200.CRF.NeuralSemiCRFInterval", "transkun_b200.LayersTransformer"]
+    assert out.stdout.split() == ["transkun_b200.CRF.NeuralSemiCRFInterval", "transkun_b200.LayersTransformer",
+                                  "transkun_b200.Util"]
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT,
+                         env=dict(os.environ, PYTHONPATH=ROOT, TKB_PATCH_SCORER="0", TKB_PATCH_FRONTEND="0"),
+                         capture_output=True, text=True, timeout=300)
+    assert out.stdout.split() == ["transkun_b200.CRF.NeuralSemiCRFInterval", "transkun.LayersTransformer", "transkun.Util"]
+
+
+def test_install_into_swaps_modules_and_keeps_the_weights():
+    """install_into() on a constructed reference model: the frontend and the scorer become ours and carry the
+    checkpoint's tensors bit for bit (same parameter / buffer names)."""
+    import pytest
+    import torch
+    sys.path.insert(0, ROOT)
+    from baseline import ref_loader
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref (the installed reference) is not present")
+    model, _ = ref_loader.load_model("cpu")
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    from transkun_b200.transcribe import install_into
+    install_into(model)
+    assert type(model.framewiseFeatureExtractor).__module__ == "transkun_b200.Util"
+    assert type(model.scorer).__module__ == "transkun_b200.LayersTransformer"
+    after = model.state_dict()
+    assert set(after) == set(before)
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+
+
+def test_tf32_split_is_exact():
+    """The 3xTF32 operand split: hi has its 13 low mantissa bits clear (TF32-exact) and hi + lo == x exactly."""
+    import torch
+    from transkun_b200.LayersTransformer import _split_tf32
+    x = torch.randn(4096) * torch.logspace(-6, 6, 4096)
+    hi, lo = _split_tf32(x)
+    assert torch.all((hi.view(torch.int32) & 8191) == 0)
+    assert torch.equal(hi + lo, x)
+    assert torch.all(lo.abs() <= x.abs() * 2.0 ** -10)

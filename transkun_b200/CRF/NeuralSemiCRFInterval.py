@@ -14,6 +14,7 @@ no CPU path: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
+import gc
 import itertools
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -231,12 +232,50 @@ def _csr(intervals, N: int, T: int, dev):
     return _csr(packed, N, T, dev)
 
 
+_pylists = None
+
+
+def _load_pylists():
+    """csrc/_tkb_pylists.so (built by transkun_b200.build from csrc/pylists.c): host-side list construction in C.
+    Not a compute path: without it the same lists are built with zip() below, three times slower."""
+    global _pylists
+    if _pylists is None:
+        import importlib.util
+        import os
+        path = os.path.join(os.path.dirname(_lib.lib_path()), "_tkb_pylists.so")
+        _pylists = False
+        if os.path.exists(path):
+            try:
+                spec = importlib.util.spec_from_file_location("_tkb_pylists", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _pylists = mod
+            except Exception:
+                _pylists = False
+    return _pylists
+
+
 def _pairs_to_lists(pairs: torch.Tensor, counts: torch.Tensor) -> Intervals:
     counts_h = counts.cpu()  # synchronises (the reference synchronises at ptr.cpu(), :56)
     maxc = int(counts_h.max()) if counts_h.numel() else 0
     if maxc == 0:
         return [[] for _ in range(pairs.shape[0])]
     pairs_h = pairs[:, :maxc].cpu().numpy()
+    # ~5e5 small objects are created here; the cyclic collector would run a young-generation pass every 700 of them
+    # for nothing (tuples of ints cannot form cycles): 40 % of the time of this function
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        return _build_lists(pairs_h, counts_h, maxc)
+    finally:
+        if gc_was_on:
+            gc.enable()
+
+
+def _build_lists(pairs_h, counts_h, maxc) -> Intervals:
+    helper = _load_pylists()
+    if helper:
+        return helper.pairs_to_lists(np.ascontiguousarray(pairs_h), counts_h.numpy(), maxc)
     # two flat int lists per track zipped into tuples: ~5x faster than tuple() over a list of 2-lists
     begins, ends = pairs_h[:, :, 0], pairs_h[:, :, 1]
     return [list(zip(begins[n, :c].tolist(), ends[n, :c].tolist())) for n, c in enumerate(counts_h.tolist())]
@@ -392,14 +431,16 @@ class NeuralSemiCRFInterval:
         """Build the object from HOST tensors (the reference's users call `.cuda()` on both first,
         crfMinimalExample.py:13-14).  Only the part of `score` the semi-CRF reads (end >= begin) is uploaded -- a
         staircase of strided 2-D copies, about half the bytes of the dense tensor; the rest of the device tensor is
-        zero.  Asynchronous on the current stream when the host tensors are pinned."""
+        left uninitialised (nothing reads it).  Asynchronous on the current stream when the host tensors are pinned."""
         device = torch.device(device)
         assert score.dim() == 3 and score.shape[0] == score.shape[1], "score must be [T, T, nBatch]"
         if score.is_cuda or noiseScore.is_cuda:
             raise RuntimeError("fromHost expects host tensors")
         T, N = score.shape[0], score.shape[2]
         s = score.detach().to(torch.float32).contiguous()
-        dev_score = torch.zeros((T, T, N), dtype=torch.float32, device=device)
+        # cells above the staircase are never read by the semi-CRF (tests/test_crf_gpu.py::test_from_host_uploads_only_what_is_read):
+        # no 1.5 GB zero fill
+        dev_score = torch.empty((T, T, N), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             rc = _lib.load().tkb_upload_lower_triangle(s.data_ptr(), dev_score.data_ptr(), T, N, rows_per_chunk,
                                                        _stream(device))

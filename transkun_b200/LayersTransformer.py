@@ -8,8 +8,17 @@ load unchanged, same forward signature `forward(ctx[B,P,T,D]) -> (S[T,T,B,P], b[
 The Linear projection (:406) is a plain library GEMM (torch/cuBLAS); everything after it -- the
 scaled q.k^T contraction, the |e-b| length factor, the diagonal and the permute into the CRF's
 [end, begin, batch, symbol] layout (:410-440) -- is ONE tcgen05/TMEM kernel (`tkb_sip_score`) that
-writes the lower triangle only (e >= b: all the semi-CRF reads; the reference fills the full square).
-TF32 operands, fp32 accumulation (the reference's own --allow_tf32 regime).
+writes the lower triangle only (e >= b: all the semi-CRF reads; the reference fills the full square; here the
+cells above the diagonal are zero).
+
+Precision follows the reference's own switch.  The reference contracts q.k^T with torch.einsum, i.e. in fp32 unless
+`torch.backends.cuda.matmul.allow_tf32` is set (train.py:41-43 sets it with --allow_tf32; transcribe.py never does).
+The tensor cores take TF32 operands, so:
+  * allow_tf32 set  -> one pass, TF32 operands / fp32 accumulation (relative error ~5e-4 per product);
+  * allow_tf32 unset (inference, the default) -> "3xTF32": q and k are split into a TF32-exact high part and a residual
+    and the kernel contracts [q_hi, q_hi, q_lo] with [k_hi, k_lo, k_hi] (three times the MMA work, ~2^-20 relative error,
+    i.e. fp32 grade).  The products are multiplied by |e-b| <= T afterwards, so the one-pass error can flip near-tie
+    Viterbi decisions against the reference; the split mode is what the config-3 parity test runs.
 """
 from __future__ import annotations
 
@@ -22,8 +31,16 @@ import torch.nn.functional as F
 from . import _lib
 
 
-def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-    """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle defined).
+def _split_tf32(x: torch.Tensor):
+    """x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32."""
+    hi = (x.view(torch.int32) & -8192).view(torch.float32)
+    return hi, x - hi
+
+
+def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.Tensor = None,
+              precise: bool = None) -> torch.Tensor:
+    """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle; zeros above).
+    precise=None follows the reference's switch: 3xTF32 unless torch.backends.cuda.matmul.allow_tf32 is set.
 
     When NT is not a multiple of 4 (the model: 90 symbols) the result is a [T, T, NT] view of a buffer whose track
     axis is padded to a multiple of 4 (strides (T*P, P, 1)): the semi-CRF sweep then keeps its 16-byte copy path
@@ -33,15 +50,23 @@ def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.T
     NT, T, D = q.shape
     assert k.shape == (NT, T, D) and diag.shape == (NT, T)
     q, k, diag = q.float().contiguous(), k.float().contiguous(), diag.float().contiguous()
+    if precise is None:
+        precise = not torch.backends.cuda.matmul.allow_tf32
     if out is None:
         P = (NT + 3) // 4 * 4
-        out = torch.zeros((T, T, P), dtype=torch.float32, device=q.device)[:, :, :NT] if P != NT else \
-            torch.empty((T, T, NT), dtype=torch.float32, device=q.device)
+        out = torch.zeros((T, T, P), dtype=torch.float32, device=q.device)[:, :, :NT]
     assert out.shape == (T, T, NT) and out.stride(2) == 1 and out.stride(0) == T * out.stride(1)
+    scale = 1.0 / math.sqrt(D)
+    if precise:
+        qh, ql = _split_tf32(q)
+        kh, kl = _split_tf32(k)
+        q = torch.cat([qh, qh, ql], dim=2)
+        k = torch.cat([kh, kl, kh], dim=2)
     with torch.cuda.device(q.device):
-        rc = _lib.load().tkb_sip_score_pitched(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, D, out.data_ptr(),
-                                               out.stride(1), torch.cuda.current_stream(q.device).cuda_stream)
-    _lib.check(rc, "tkb_sip_score_pitched")
+        rc = _lib.load().tkb_sip_score_scaled(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, q.shape[2], scale,
+                                              out.data_ptr(), out.stride(1),
+                                              torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(rc, "tkb_sip_score_scaled")
     return out
 
 

@@ -114,10 +114,17 @@ class MelSpectrum(nn.Module):
             raise RuntimeError("transkun_b200 has no CPU path: frames must be a CUDA tensor")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("frontend training path (gradients of the window parameters) not implemented")
-        squeeze = frames.dim() == 3
-        if squeeze:
+        # the reference accepts any leading shape [..., nFrame, windowSize]; with toMono it averages dim -4 of the
+        # [..., nFrame, nFreq, nWin] spectrum whenever that has >= 4 dims (Util.py:158-159), i.e. the dim right before
+        # nFrame of the input whenever the input has >= 3 dims (keepdim=True)
+        lead = frames.shape[:-2]
+        if frames.dim() == 2:
+            frames = frames[None, None]
+        elif frames.dim() == 3:
             frames = frames.unsqueeze(0)
-        assert frames.dim() == 4, "frames must be [B, C, nFrame, windowSize] (or [C, nFrame, windowSize])"
+        elif frames.dim() > 4:
+            frames = frames.reshape(-1, *frames.shape[-3:])
+        assert frames.dim() == 4
         if frames.dtype != torch.float32 or frames.stride(-1) != 1:
             frames = frames.float().contiguous()
         B, C, Fr, W = frames.shape
@@ -125,7 +132,7 @@ class MelSpectrum(nn.Module):
             wins = self.spectrogramExtractor.windows().float()
         nWin, nMel = wins.shape[0], self.freq2mels.shape[1]
         lo, cnt = self._band_tables()
-        mono = 1 if (self.toMono and not squeeze) else 0  # the reference averages dim -4 only for >= 4-D spectra
+        mono = 1 if (self.toMono and len(lead) >= 1) else 0
         L = _lib.load()
         ws = torch.empty(L.tkb_logmel_workspace_bytes(B, C, Fr, W, nWin), dtype=torch.uint8, device=frames.device)
         out = torch.empty((B, 1 if mono else C, Fr, nMel, nWin), dtype=torch.float32, device=frames.device)
@@ -135,4 +142,6 @@ class MelSpectrum(nn.Module):
                               float(self.eps), out.data_ptr(), ws.data_ptr(),
                               torch.cuda.current_stream(frames.device).cuda_stream)
         _lib.check(rc, "tkb_logmel")
-        return out[0] if squeeze else out
+        if len(lead) >= 1:
+            lead = lead[:-1] + ((1,) if mono else (lead[-1],))
+        return out.reshape(*lead, Fr, nMel, nWin)

@@ -30,6 +30,8 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
     """Compiles every .cu to an object file in parallel (the two sweep kernels dominate), then links."""
+    if out == LIB:
+        build_pylists(force)
     if not force and out == LIB and not needs_build():
         return LIB
     import concurrent.futures
@@ -60,6 +62,22 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if verbose:
         print("".join(log))
     return out
+
+
+PYLISTS = os.path.join(CSRC, "_tkb_pylists.so")
+
+
+def build_pylists(force: bool = False) -> str:
+    """Host-side CPython helper (csrc/pylists.c): packed decode result -> the reference's list-of-lists-of-tuples."""
+    import sysconfig
+    src = os.path.join(CSRC, "pylists.c")
+    if not force and os.path.exists(PYLISTS) and os.path.getmtime(PYLISTS) >= os.path.getmtime(src):
+        return PYLISTS
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], src, "-o", PYLISTS]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return PYLISTS
 
 
 def build_timeline() -> str:

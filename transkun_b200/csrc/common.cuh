@@ -12,6 +12,15 @@ namespace tkb {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);  // records the error, returns (int)e
 
+// Function attributes (dynamic shared memory opt-in) and cuFFT plans are PER DEVICE: caches of "already configured"
+// are indexed by the current device, never kept in a single per-process flag.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+
 #define TKB_CUDA(call)                                          \
     do {                                                        \
         cudaError_t _e = (call);                                \

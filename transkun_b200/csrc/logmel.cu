@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) mel_log_kernel(const float2 *__restrict__
 }
 
 struct PlanEntry {
-    int n, batch;
+    int n, batch, dev;  // a cuFFT plan belongs to the device it was made on
     cufftHandle plan;
     size_t work;
 };
@@ -68,8 +68,9 @@ static PlanEntry g_plans[8];
 static int g_nplans = 0;
 
 static int get_plan(int n, int batch, PlanEntry **out) {
+    const int dev = current_device();
     for (int i = 0; i < g_nplans; ++i)
-        if (g_plans[i].n == n && g_plans[i].batch == batch) {
+        if (g_plans[i].n == n && g_plans[i].batch == batch && g_plans[i].dev == dev) {
             *out = &g_plans[i];
             return 0;
         }
@@ -81,6 +82,7 @@ static int get_plan(int n, int batch, PlanEntry **out) {
     PlanEntry e;
     e.n = n;
     e.batch = batch;
+    e.dev = dev;
     if (cufftCreate(&e.plan) != CUFFT_SUCCESS || cufftSetAutoAllocation(e.plan, 0) != CUFFT_SUCCESS) {
         set_error("cufftCreate failed");
         return TKB_ENODEV;
@@ -138,7 +140,10 @@ extern "C" int tkb_logmel(const float *frames, int64_t stride_b, int64_t stride_
         return TKB_ENODEV;
     }
     const size_t smem = (size_t)nWin * nFreq * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_by_dev[kMaxDevices] = {};
+    const int dev_ = current_device();
+    size_t dummy_ = 0;
+    size_t &configured = dev_ >= 0 ? configured_by_dev[dev_] : dummy_;
     if (smem > 48 * 1024 && smem > configured) {
         TKB_CUDA(cudaFuncSetAttribute(mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

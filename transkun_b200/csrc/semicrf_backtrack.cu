@@ -135,7 +135,10 @@ static int launch_backtrack(const uint32_t *code, int T, int N, const int32_t *f
         set_error("tkb_semicrf_backtrack: T=%d exceeds the shared-memory walk (max T ~ 17000)", T);
         return TKB_EINVAL;
     }
-    static size_t configured = 0;
+    static size_t configured_by_dev[kMaxDevices] = {};
+    const int dev_ = current_device();
+    size_t dummy_ = 0;
+    size_t &configured = dev_ >= 0 ? configured_by_dev[dev_] : dummy_;
     if (smem > 48 * 1024 && smem > configured) {
         TKB_CUDA(cudaFuncSetAttribute(backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

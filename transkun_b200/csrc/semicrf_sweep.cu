@@ -849,8 +849,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-constexpr int kMaxDevices = 64;
-
 template <int DIR, int ALIGN, int MODE>
 static int launch_one(const SweepParams &p, const CUtensorMap &map, int grid, cudaStream_t stream) {
     auto kern = sweep_kernel<DIR, ALIGN, MODE>;

@@ -272,16 +272,22 @@ extern "C" int tkb_sip_score(const float *q, const float *k, const float *diag, 
 
 extern "C" int tkb_sip_score_pitched(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
                                      float *out_score, int64_t pitch, void *stream_) {
+    return tkb_sip_score_scaled(q, k, diag, n_tracks, T, D, D > 0 ? 1.0f / sqrtf((float)D) : 0.0f, out_score, pitch, stream_);
+}
+
+extern "C" int tkb_sip_score_scaled(const float *q, const float *k, const float *diag, int n_tracks, int T, int D,
+                                    float scale, float *out_score, int64_t pitch, void *stream_) {
     if (!q || !k || !diag || !out_score || n_tracks < 1 || T < 1 || D < SC_KC || D % SC_KC != 0 || pitch < n_tracks ||
         (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15)) {
         set_error("tkb_sip_score: invalid argument (tracks=%d T=%d D=%d; D must be a multiple of 32, q/k 16-byte aligned)",
                   n_tracks, T, D);
         return TKB_EINVAL;
     }
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0 || !configured[dev]) {
         TKB_CUDA(cudaFuncSetAttribute(sip_scorer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScorerSmem));
-        configured = true;
+        if (dev >= 0) configured[dev] = true;
     }
     ScorerParams p;
     p.q = q;
@@ -292,7 +298,7 @@ extern "C" int tkb_sip_score_pitched(const float *q, const float *k, const float
     p.pitch = pitch;
     p.T = T;
     p.D = D;
-    p.qscale = 1.0f / sqrtf((float)D);
+    p.qscale = scale;
     const int neb = (T + SC_TE - 1) / SC_TE, nbb = (T + SC_TB - 1) / SC_TB;
     long long tiles = 0;
     for (int eb = 0; eb < neb; ++eb) tiles += (2 * eb + 2 < nbb) ? 2 * eb + 2 : nbb;
