@@ -115,4 +115,4 @@ class Golden:
 def golden_cases(prefix: str = ""):
     """Semi-CRF fixtures only (the scorer_* / frontend_* files belong to their own tests)."""
     return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz"))
-                  if not os.path.basename(p).startswith(("scorer_", "frontend_", "config3_")))
+                  if not os.path.basename(p).startswith(("scorer_", "frontend_", "config3_", "gradbig_")))

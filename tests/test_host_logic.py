@@ -51,3 +51,23 @@ def test_padded_track_axis_predicate():
     odd = torch.zeros(T, N, T).permute(0, 2, 1)
     assert _prep_score_for_sweep(odd).is_contiguous()
     assert _prep_score_for_sweep(dense.double()).dtype == torch.float32
+
+
+def test_packed_intervals_are_validated_once():
+    """A PackedIntervals object is checked when it is built (endpoints >= 0, begin <= end, CSR offsets) and against T when
+    it is used: the kernels index score[end, begin] with these values."""
+    import pytest
+    import torch
+    from transkun_b200.CRF.NeuralSemiCRFInterval import PackedIntervals, _csr, pack_intervals
+    ok = pack_intervals([[(0, 2), (4, 6)], [], [(3, 3)]], T=8)
+    assert ok.max_endpoint == 6
+    with pytest.raises(IndexError):
+        _csr(ok, 3, 6, torch.device("cpu"))          # endpoint 6 with T = 6
+    with pytest.raises(ValueError):
+        _csr(ok, 2, 8, torch.device("cpu"))          # three lists for two tracks
+    with pytest.raises(ValueError):
+        PackedIntervals(torch.tensor([[5, 2]]), torch.tensor([0, 1]))      # begin > end
+    with pytest.raises(IndexError):
+        PackedIntervals(torch.tensor([[-1, 2]]), torch.tensor([0, 1]))
+    with pytest.raises(ValueError):
+        PackedIntervals(torch.tensor([[1, 2]]), torch.tensor([0, 2]))      # offsets past the pairs

@@ -203,6 +203,20 @@ class PackedIntervals:
         assert pairs.dim() == 2 and pairs.shape[1] == 2 and offsets.dim() == 1
         self.pairs = pairs.to(torch.int32).contiguous()
         self.offsets = offsets.to(torch.int64).contiguous()
+        # validated once, here: the kernels index score[end, begin] and the dense gradient with these values (the
+        # reference's gather would raise an index error; an unchecked kernel would read and atomicAdd out of bounds)
+        if self.pairs.numel():
+            lo, hi = int(self.pairs.min()), int(self.pairs.max())
+            if lo < 0:
+                raise IndexError("interval endpoints must be >= 0")
+            if bool((self.pairs[:, 0] > self.pairs[:, 1]).any()):
+                raise ValueError("intervals must satisfy begin <= end")
+            self.max_endpoint = hi
+        else:
+            self.max_endpoint = -1
+        if self.offsets.numel() < 1 or int(self.offsets[0]) != 0 or int(self.offsets[-1]) != self.pairs.shape[0] or \
+                bool((self.offsets[1:] < self.offsets[:-1]).any()):
+            raise ValueError("offsets must be a CSR row-pointer array over pairs")
 
 
 def pack_intervals(intervals: Intervals, T: Optional[int] = None) -> PackedIntervals:
@@ -222,6 +236,8 @@ def _csr(intervals, N: int, T: int, dev):
     if isinstance(intervals, PackedIntervals):
         if intervals.offsets.numel() != N + 1:
             raise ValueError(f"intervals must have one list per track ({N}), got {intervals.offsets.numel() - 1}")
+        if intervals.max_endpoint >= T:
+            raise IndexError("interval endpoints must lie in [0, T)")
         pairs = intervals.pairs.to(dev, non_blocking=True)
         if pairs.numel() == 0:
             pairs = torch.zeros((1, 2), dtype=torch.int32, device=dev)
