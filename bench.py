@@ -239,7 +239,7 @@ def run_ours(args):
     from transkun_b200 import _lib
     from transkun_b200.CRF.NeuralSemiCRFInterval import NeuralSemiCRFInterval, backtrack_records, sweep
     from transkun_b200._lib import BACKWARD, SWEEP_LOGSUM, SWEEP_VITERBI
-    from transkun_b200.sharded import PushGather, gather_records, track_shard
+    from transkun_b200.sharded import FusedPushGather, PushGather, gather_records, track_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -269,19 +269,24 @@ def run_ours(args):
     # symmetric memory on a side stream, overlapped with the next step's sweep (transkun_b200.sharded.PushGather);
     # fallback: one NCCL all-gather per step on the compute stream.
     push = None
+    fused = None
+    mode = os.environ.get("TKB_GATHER", "fused")
     # (needs every rank to own the same number of tracks: 88 splits evenly over 2, 4 and 8 GPUs)
-    if world > 1 and n_total % world == 0 and os.environ.get("TKB_GATHER", "push") == "push":
+    if world > 1 and n_total % world == 0 and mode in ("fused", "push"):
         try:
-            push = PushGather(n_local, 2 + 4 * T, dev)
+            if mode == "fused":
+                fused = FusedPushGather(n_local, T, dev)
+            else:
+                push = PushGather(n_local, 2 + 4 * T, dev)
         except Exception as exc:  # no symmetric memory / P2P: NCCL path
             if rank == 0:
                 print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
-            push = None
+            push = fused = None
     if world > 1:  # every rank must take the same path
-        agree = torch.tensor([1 if push is not None else 0], device=dev)
+        agree = torch.tensor([1 if (push is not None or fused is not None) else 0], device=dev)
         dist.all_reduce(agree, op=dist.ReduceOp.MIN)
         if int(agree.item()) == 0:
-            push = None
+            push = fused = None
 
     def step(record=False):
         if record:
@@ -291,6 +296,12 @@ def run_ours(args):
         if record:
             e1.record(stream)
             ev_sweep.append((e0, e1))
+        if fused is not None:
+            # back-track + NVLink push of the records in one kernel.  The gather of step k is complete when all ranks'
+            # flags of step k are in; waiting for them one step later (step k-1 here) keeps the ranks out of lock-step:
+            # the exchange of a step overlaps the next sweep, as with the copy-engine variant
+            st = fused.submit(code, None, BACKWARD, lse[0])
+            return fused.result(st - 1) if st > 1 else None
         rec = backtrack_records(code, None, BACKWARD, lse[0])  # [count, logZ, pairs] per track
         if push is not None:
             return push.result(push.submit(rec))  # complete once the stream has passed push.wait()
@@ -299,20 +310,26 @@ def run_ours(args):
         return rec
 
     def fence():
+        if fused is not None and fused.step > 0:
+            fused.result(fused.step)  # the last step's exchange has landed everywhere
         if push is not None:
             push.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    if push is not None:  # once, untimed: the pushed gather equals the NCCL gather
+    if push is not None or fused is not None:  # once, untimed: the pushed gather equals the NCCL gather
         code0, _, lse0, _ = sweep(score, noise, BACKWARD, SWEEP_VITERBI | SWEEP_LOGSUM)
         rec0 = backtrack_records(code0, None, BACKWARD, lse0[0])
         want = gather_records(rec0, n_total)
-        got = push.result(push.submit(rec0))
-        push.wait()
+        if fused is not None:
+            got = fused.result(fused.submit(code0, None, BACKWARD, lse0[0]))
+        else:
+            got = push.result(push.submit(rec0))
+            push.wait()
         torch.cuda.synchronize(dev)
-        assert torch.equal(got, want), "pushed gather differs from the NCCL gather"
+        live = torch.arange(want.shape[1], device=dev)[None, :] < (2 + 2 * want[:, :1])   # count, logZ, live pairs
+        assert torch.equal(torch.where(live, got, 0), torch.where(live, want, 0)), "pushed gather differs from the NCCL gather"
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -324,6 +341,8 @@ def run_ours(args):
         step(record=True)
     if push is not None:
         push.wait()  # the timed region ends when the last exchange has landed everywhere
+    if fused is not None:
+        fused.result(fused.step)
     t1.record(stream)
     fence()
     ms = t0.elapsed_time(t1)
@@ -429,8 +448,11 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(T, n_local, n_total, world),
-            "exchange": ("none" if world == 1 else ("copy-engine pushes into symmetric memory, overlapped with the "
-                         "next sweep" if push is not None else "NCCL all-gather per step")),
+            "exchange": ("none" if world == 1 else (
+                "fused: the back-track kernel stores every record into all ranks' symmetric (NVLink peer) buffers and "
+                "publishes a step flag" if fused is not None else (
+                    "copy-engine pushes into symmetric memory, overlapped with the next sweep" if push is not None
+                    else "NCCL all-gather per step"))),
             "e2e": {"value": cells_per_step / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3, "breakdown": bd,
                     "api": "NeuralSemiCRFInterval.fromHost(score, noise, device).decodeWithLogZ() from pinned host tensors "

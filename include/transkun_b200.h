@@ -134,6 +134,24 @@ int tkb_semicrf_backtrack_strided(const uint32_t *code, int T, int N, const int3
                                   int32_t *out_counts, int64_t count_stride, void *stream);
 
 /*
+ * Back-tracking FUSED WITH THE MULTI-GPU EXCHANGE of a track-sharded problem (the reference has
+ * no counterpart: it decodes all 90 symbols on one device, ModelTransformer.py:549).  Rank `rank` of `world` decodes its N
+ * tracks and stores every track's record
+ *     int32 record[record_stride] = { count, logZ bits (0 if logz is NULL), begin_0, end_0, begin_1, end_1, ... }
+ * at row rank*N + n of the record buffer of EVERY rank -- peer_records[r] (HOST array of `world` DEVICE pointers, peer-mapped
+ * symmetric memory, [world*N][record_stride] int32, 8-byte aligned, record_stride even and >= 2 + 4*T) -- then publishes
+ * peer_flags[r][rank] = step (HOST array of `world` DEVICE pointers to uint32[world]) with system-scope release once all
+ * its stores are performed.  `step` counts 1, 2, ...; from step 2 on the kernel first waits until every rank has
+ * published step-1, which tells it that the buffer it is about to overwrite (callers alternate two buffers) is no longer
+ * read.  ticket: DEVICE uint32, zero on first use; status: DEVICE int32, receives `step` if a wait times out (4 s).
+ * tkb_wait_flags is the consumer side: one tiny kernel that returns once flags[0..world) >= step.
+ */
+int tkb_semicrf_backtrack_push(const uint32_t *code, int T, int N, const int32_t *forced_start, int direction,
+                               const float *logz, void *const *peer_records, void *const *peer_flags, int world, int rank,
+                               int64_t record_stride, uint32_t step, uint32_t *ticket, int32_t *status, void *stream);
+int tkb_wait_flags(const uint32_t *flags, int world, uint32_t step, int32_t *status, void *stream);
+
+/*
  * Marginals (the custom gradient of the log-partition).  Replaces
  *   CRF/NeuralSemiCRFInterval.py:417-447 (forward_backward) fused with
  *   CRF/NeuralSemiCRFInterval.py:469-472 (ComputeLogZFasterGrad.backward).

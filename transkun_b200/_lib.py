@@ -20,7 +20,7 @@ SWEEP_VITERBI, SWEEP_LOGSUM = 1, 2
 EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
     "tkb_semicrf_sweep_pitched",
-    "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
+    "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_backtrack_push", "tkb_wait_flags", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
     "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_sip_score_pitched", "tkb_sip_score_scaled", "tkb_logmel_workspace_bytes", "tkb_logmel",
     "tkb_upload_lower_triangle",
 )
@@ -68,6 +68,11 @@ def load() -> ctypes.CDLL:
     L.tkb_semicrf_backtrack.argtypes = [vp, i, i, vp, i, vp, vp, vp]
     L.tkb_semicrf_backtrack_strided.restype = i
     L.tkb_semicrf_backtrack_strided.argtypes = [vp, i, i, vp, i, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]
+    L.tkb_semicrf_backtrack_push.restype = i
+    L.tkb_semicrf_backtrack_push.argtypes = [vp, i, i, vp, i, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i, i,
+                                             ctypes.c_int64, u32, vp, vp, vp]
+    L.tkb_wait_flags.restype = i
+    L.tkb_wait_flags.argtypes = [vp, i, u32, vp, vp]
     L.tkb_semicrf_marginals.restype = i
     L.tkb_semicrf_marginals.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     L.tkb_semicrf_evalpath.restype = i

@@ -12,8 +12,17 @@
 // visited position writes its (begin,end) pairs straight to its slot -- in
 // exactly the order the reference appends them (and reversed for FORWARD, :196).
 //
+// backtrack_push_kernel is the same walk FUSED WITH THE MULTI-GPU EXCHANGE: the tracks of a sharded
+// problem are decoded on different GPUs and every rank needs all decoded intervals.  Instead of decoding into local
+// memory and running an all-gather afterwards, each CTA stores its track's record {count, logZ, pairs} straight into
+// the symmetric (peer-mapped, NVLink) record buffer of EVERY rank, and the last CTA of the grid publishes a per-rank
+// step flag with system-scope release: no collective kernel, no copy-engine traffic, no barrier kernels, and the next
+// sweep can start as soon as this kernel has issued its stores.
+//
 // Mirrored walk coordinate u: BACKWARD u = position; FORWARD u = T-1-position.
 // The walk always runs u = start .. T-1 upwards and ends at u = T-1.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace tkb {
@@ -30,10 +39,24 @@ __device__ __forceinline__ T warp_scan_incl(T v, int lane) {
     return v;
 }
 
+constexpr int kMaxPeers = 16;
+struct PushDst {
+    int *rec[kMaxPeers];            // record buffers of the ranks, [world * N][stride] int32 each
+    unsigned *flag[kMaxPeers];      // step flags of the ranks, [world] uint32 each
+    const float *logz;              // [N] or null
+    unsigned *ticket;               // local counter, zero between launches
+    int *status;                    // local status word (0, or the step whose wait timed out)
+    int world, rank;
+    unsigned step;                  // 1, 2, ...
+    long long stride;               // ints per record: 2 + 4*T at least
+};
+
+template <bool PUSH>
 __global__ void __launch_bounds__(BT_THREADS) backtrack_kernel(const unsigned *__restrict__ code, int T, int N,
                                                                const int *__restrict__ forced, int dir,
                                                                int *__restrict__ pairs, int *__restrict__ counts,
-                                                               long long pair_stride, long long count_stride) {
+                                                               long long pair_stride, long long count_stride,
+                                                               const PushDst dst) {
     extern __shared__ int sm[];
     int *nxtA = sm;              // [T]
     int *nxtB = sm + T;          // [T]
@@ -96,26 +119,103 @@ __global__ void __launch_bounds__(BT_THREADS) backtrack_kernel(const unsigned *_
         total += t;
     }
     int k = woff + incl - local;
-    int *out = pairs + (size_t)n * pair_stride;
+    if (PUSH) {
+        // The slot this step writes was last written two steps ago; every rank may have been reading it until it
+        // submitted the step in between, which is what its flag of step-1 says (transkun_b200.sharded.FusedPushGather).
+        if (tid == 0 && dst.step >= 2) {
+            const volatile unsigned *mine = dst.flag[dst.rank];
+            unsigned long long t0 = 0;
+            for (unsigned tries = 0;; ++tries) {
+                bool ok = true;
+                for (int r = 0; r < dst.world; ++r) ok &= (int)(mine[r] - (dst.step - 1)) >= 0;
+                if (ok) break;
+                if ((tries & 255) == 255) {
+                    if (t0 == 0) t0 = globaltimer_ns();
+                    if (globaltimer_ns() - t0 > 4000000000ull) {
+                        atomicExch(dst.status, (int)dst.step);
+                        break;
+                    }
+                }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
+    int2 *stage = reinterpret_cast<int2 *>(sm + 4 * T);   // PUSH: [2T] pairs staged in shared memory (8-byte aligned)
+    auto emit = [&](int slot, int b, int e) {
+        if (PUSH) {
+            stage[slot] = make_int2(b, e);
+        } else {
+            int *out = pairs + (size_t)n * pair_stride;
+            out[2 * slot] = b;
+            out[2 * slot + 1] = e;
+        }
+    };
     for (int u = ubeg; u < uend; ++u)
         if (mark[u]) {
             const unsigned w = cw[u];
             const int posn = (dir == TKB_BACKWARD) ? u : T - 1 - u;
             if (w & 1u) {
-                const int slot = (dir == TKB_BACKWARD) ? k : total - 1 - k;
-                out[2 * slot] = posn;
-                out[2 * slot + 1] = posn;
+                emit((dir == TKB_BACKWARD) ? k : total - 1 - k, posn, posn);
                 ++k;
             }
             if (u < T - 1 && (w >> 1) != 0) {
                 const int sel = (int)(w >> 1) - 1;
-                const int slot = (dir == TKB_BACKWARD) ? k : total - 1 - k;
-                out[2 * slot] = (dir == TKB_BACKWARD) ? posn : sel;  // (begin, end)
-                out[2 * slot + 1] = (dir == TKB_BACKWARD) ? sel : posn;
+                // (begin, end)
+                emit((dir == TKB_BACKWARD) ? k : total - 1 - k, (dir == TKB_BACKWARD) ? posn : sel,
+                     (dir == TKB_BACKWARD) ? sel : posn);
                 ++k;
             }
         }
-    if (tid == 0) counts[(size_t)n * count_stride] = total;
+    if (!PUSH) {
+        if (tid == 0) counts[(size_t)n * count_stride] = total;
+        return;
+    }
+    __syncthreads();
+    {
+        // the record {count, logZ, pairs} goes to every rank with coalesced 8-byte stores (consecutive threads,
+        // consecutive pairs): local memory for this rank, NVLink peer stores for the others
+        const long long o = ((long long)dst.rank * N + n) * dst.stride;
+        const int2 head = make_int2(total, dst.logz ? __float_as_int(dst.logz[n]) : 0);
+        for (int r = 0; r < dst.world; ++r) {
+            int2 *out = reinterpret_cast<int2 *>(dst.rec[r] + o);
+            if (tid == 0) out[0] = head;
+            for (int i = tid; i < total; i += BT_THREADS) out[1 + i] = stage[i];
+        }
+    }
+    // every store of this CTA is performed system-wide before its ticket; the CTA that takes the last ticket
+    // publishes this rank's step flag on every rank
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(dst.ticket, 1u);
+        if (t == (unsigned)N - 1) {
+            *dst.ticket = 0;   // ready for the next launch (stream order)
+            __threadfence_system();
+            for (int r = 0; r < dst.world; ++r)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst.flag[r] + dst.rank), "r"(dst.step) : "memory");
+        }
+    }
+}
+
+// waits until every rank's flag has reached `step` (one thread; the consumer side of backtrack_push_kernel)
+__global__ void wait_flags_kernel(const unsigned *flags, int world, unsigned step, int *status) {
+    const volatile unsigned *f = flags;
+    unsigned long long t0 = 0;
+    for (unsigned tries = 0;; ++tries) {
+        bool ok = true;
+        for (int r = 0; r < world; ++r) ok &= (int)(f[r] - step) >= 0;
+        if (ok) break;
+        if ((tries & 255) == 255) {
+            if (t0 == 0) t0 = globaltimer_ns();
+            if (globaltimer_ns() - t0 > 4000000000ull) {
+                atomicExch(status, (int)step);
+                break;
+            }
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();   // acquire: the records written before the flags are visible to what follows on the stream
 }
 
 }  // namespace tkb
@@ -140,11 +240,69 @@ static int launch_backtrack(const uint32_t *code, int T, int N, const int32_t *f
     size_t dummy_ = 0;
     size_t &configured = dev_ >= 0 ? configured_by_dev[dev_] : dummy_;
     if (smem > 48 * 1024 && smem > configured) {
-        TKB_CUDA(cudaFuncSetAttribute(backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TKB_CUDA(cudaFuncSetAttribute(backtrack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TKB_CUDA(cudaFuncSetAttribute(backtrack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    backtrack_kernel<<<N, BT_THREADS, smem, (cudaStream_t)stream_>>>(code, T, N, forced_start, direction, out_pairs,
-                                                                     out_counts, pair_stride, count_stride);
+    PushDst none;
+    memset(&none, 0, sizeof(none));
+    backtrack_kernel<false><<<N, BT_THREADS, smem, (cudaStream_t)stream_>>>(code, T, N, forced_start, direction, out_pairs,
+                                                                            out_counts, pair_stride, count_stride, none);
+    TKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tkb_semicrf_backtrack_push(const uint32_t *code, int T, int N, const int32_t *forced_start, int direction,
+                                          const float *logz, void *const *peer_records, void *const *peer_flags, int world,
+                                          int rank, int64_t record_stride, uint32_t step, uint32_t *ticket, int32_t *status,
+                                          void *stream_) {
+    if (!code || !peer_records || !peer_flags || !ticket || !status || T < 1 || N < 1 || world < 1 || world > kMaxPeers ||
+        rank < 0 || rank >= world || record_stride < 2 + 4ll * T || (record_stride & 1) || step == 0 ||
+        (direction != TKB_BACKWARD && direction != TKB_FORWARD)) {
+        set_error("tkb_semicrf_backtrack_push: invalid argument (T=%d N=%d world=%d rank=%d stride=%lld step=%u)", T, N,
+                  world, rank, (long long)record_stride, step);
+        return TKB_EINVAL;
+    }
+    const size_t smem = (size_t)T * 4 * sizeof(int) + (size_t)2 * T * sizeof(int2);   // walk tables + staged pairs
+    if (smem > 220 * 1024) {
+        set_error("tkb_semicrf_backtrack_push: T=%d exceeds the shared-memory walk (max T ~ 7000)", T);
+        return TKB_EINVAL;
+    }
+    static size_t configured_by_dev[kMaxDevices] = {};
+    const int dev_ = current_device();
+    if (smem > 48 * 1024 && (dev_ < 0 || smem > configured_by_dev[dev_])) {
+        TKB_CUDA(cudaFuncSetAttribute(backtrack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev_ >= 0) configured_by_dev[dev_] = smem;
+    }
+    PushDst d;
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < world; ++r) {
+        if (!peer_records[r] || !peer_flags[r]) {
+            set_error("tkb_semicrf_backtrack_push: null peer pointer for rank %d", r);
+            return TKB_EINVAL;
+        }
+        d.rec[r] = reinterpret_cast<int *>(peer_records[r]);
+        d.flag[r] = reinterpret_cast<unsigned *>(peer_flags[r]);
+    }
+    d.logz = logz;
+    d.ticket = ticket;
+    d.status = status;
+    d.world = world;
+    d.rank = rank;
+    d.step = step;
+    d.stride = record_stride;
+    backtrack_kernel<true><<<N, BT_THREADS, smem, (cudaStream_t)stream_>>>(code, T, N, forced_start, direction, nullptr,
+                                                                           nullptr, 0, 0, d);
+    TKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tkb_wait_flags(const uint32_t *flags, int world, uint32_t step, int32_t *status, void *stream_) {
+    if (!flags || !status || world < 1 || world > kMaxPeers) {
+        set_error("tkb_wait_flags: invalid argument (world=%d)", world);
+        return TKB_EINVAL;
+    }
+    wait_flags_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(flags, world, step, status);
     TKB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -147,3 +147,72 @@ class PushGather:
         for ev in self.done:
             if ev is not None:
                 cur.wait_event(ev)
+
+
+class FusedPushGather:
+    """Decode + all-gather in ONE kernel: `tkb_semicrf_backtrack_push` back-tracks this rank's tracks and stores every
+    track's record {count, logZ, pairs} straight into the symmetric (peer-mapped, NVLink) record buffer of every rank,
+    then publishes a per-rank step flag; `result()` enqueues a one-thread kernel that waits for all ranks' flags.  No
+    collective kernel, no copy engines, no barrier kernels: the next sweep starts as soon as the back-track has issued
+    its stores.  Two record buffers alternate by step parity; the records of step k stay valid until submit(k+2), and a
+    caller must have enqueued its reads of step k before it calls submit(k+1) (the kernel of step k+2 waits for every
+    rank's flag of step k+1 before it overwrites the buffer).  Requires the same number of tracks on every rank and
+    torch symmetric memory (one node, P2P)."""
+
+    def __init__(self, n_local: int, T: int, device: torch.device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n_local, self.T, self.R = n_local, T, 2 + 4 * T
+        self.device = device
+        slot_ints = self.world * n_local * self.R
+        self.flag_off = 2 * slot_ints                      # int32 index of the flags inside the symmetric buffer
+        total = self.flag_off + 64
+        self.buf = symm_mem.empty((total,), dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)                        # everybody's flags are zero before anybody pushes
+        bases = [int(p) for p in self.hdl.buffer_ptrs]
+        vp = ctypes.c_void_p
+        self.rec_ptrs = [(vp * self.world)(*[b + 4 * s * slot_ints for b in bases]) for s in (0, 1)]
+        self.flag_ptrs = (vp * self.world)(*[b + 4 * self.flag_off for b in bases])
+        self.local = torch.zeros((16,), dtype=torch.int32, device=device)   # [0] ticket, [8] status
+        self.step = 0
+        self.slot_ints = slot_ints
+
+    def submit(self, code: torch.Tensor, forced, direction: int, logz=None) -> int:
+        """Back-track `code` [n_local, T] and push the records of this step; returns the step number."""
+        assert code.shape == (self.n_local, self.T)
+        self.step += 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if logz is not None:
+            logz = logz.contiguous()
+        with torch.cuda.device(self.device):
+            rc = self._lib.load().tkb_semicrf_backtrack_push(
+                code.data_ptr(), self.T, self.n_local, None if forced is None else forced.data_ptr(), direction,
+                None if logz is None else logz.data_ptr(), self.rec_ptrs[self.step & 1], self.flag_ptrs, self.world,
+                self.rank, self.R, self.step, self.local.data_ptr(), self.local.data_ptr() + 32, stream)
+        self._lib.check(rc, "tkb_semicrf_backtrack_push")
+        self._keep = (code, forced, logz)   # alive until the kernel has run
+        return self.step
+
+    def result(self, step: int) -> torch.Tensor:
+        """[world * n_local, 2 + 4T] records of `step` (tracks in global order), valid on the current stream after the
+        flag wait enqueued here."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self._lib.load().tkb_wait_flags(self.buf.data_ptr() + 4 * self.flag_off, self.world, step,
+                                                 self.local.data_ptr() + 32, stream)
+        self._lib.check(rc, "tkb_wait_flags")
+        s = step & 1
+        return self.buf[s * self.slot_ints:(s + 1) * self.slot_ints].view(self.world * self.n_local, self.R)
+
+    def timed_out(self) -> bool:
+        """True if a flag wait gave up (synchronises)."""
+        return int(self.local[8].item()) != 0
