@@ -63,3 +63,16 @@ m = install_into(copy.deepcopy(model_ref), patch_scorer=True, patch_frontend=Tru
 run(m, x)
 notes, t = run(m, x, reps=3)
 print(f"all three, one-pass TF32 scorer (allow_tf32): {t*1e3:.0f} ms;", diff(notes_ref, notes), flush=True)
+
+# ---- batched segment pipeline (transkun_b200.batched): same notes, far fewer launches ----
+torch.backends.cuda.matmul.allow_tf32 = False
+from transkun_b200.batched import transcribe_batched  # noqa: E402
+m = install_into(copy.deepcopy(model_ref), patch_scorer=True, patch_frontend=True)
+for mb in (4, 8, 16):
+    transcribe_batched(m, x, max_batch=mb)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(3):
+        notes_b = transcribe_batched(m, x, max_batch=mb)
+    torch.cuda.synchronize()
+    print(f"batched segments (max_batch={mb}): {(time.time() - t0) / 3 * 1e3:.0f} ms;", diff(notes_ref, notes_b), flush=True)

@@ -95,3 +95,34 @@ def test_notes_against_the_reference_cpu_fixture(reference_model, name, seconds,
     have = set((n.pitch, int(round(n.start / 2e-3)), int(round(n.end / 2e-3))) for n in got)
     missing, extra = want - have, have - want
     assert len(missing) <= 0.02 * len(want) + 1 and len(extra) <= 0.02 * len(want) + 1, (len(want), sorted(missing), sorted(extra))
+
+
+def test_batched_segments_give_the_reference_notes(reference_model):
+    """transkun_b200.batched.transcribe_batched: the network, scorer and ONE semi-CRF sweep over all segments of a chunk,
+    the reference's own loop for the sequential rest (forced start positions, event merging) -- same notes as the
+    untouched reference transcribing segment by segment (40 s of audio = 7 segments; chunks of 3 and of 8)."""
+    from transkun_b200.batched import transcribe_batched
+    from transkun_b200.transcribe import install_into
+    import transkun.ModelTransformer as MT
+    ref_crf = _reference_crf_class()
+
+    class _RefCRF:
+        NeuralSemiCRFInterval = ref_crf
+
+    x = torch.from_numpy(ref_loader.synthetic_audio(40.0, seed=5)).cuda()
+    saved = MT.CRF
+    MT.CRF = _RefCRF
+    try:
+        with torch.no_grad():
+            want = reference_model.transcribe(x)
+    finally:
+        MT.CRF = saved
+    ours = install_into(copy.deepcopy(reference_model))
+    for max_batch in (3, 8):
+        got = transcribe_batched(ours, x, max_batch=max_batch)
+        assert len(got) == len(want) > 50
+        assert [(n.pitch, n.velocity, n.hasOnset, n.hasOffset) for n in got] == \
+            [(n.pitch, n.velocity, n.hasOnset, n.hasOffset) for n in want]
+        np.testing.assert_allclose([n.start for n in got], [n.start for n in want], rtol=0, atol=1e-4)
+        np.testing.assert_allclose([n.end for n in got], [n.end for n in want], rtol=0, atol=1e-4)
+    assert "processFramesBatch" not in ours.__dict__   # the temporary override is gone

@@ -476,17 +476,30 @@ class NeuralSemiCRFInterval:
         score.device, nothing synchronised.  with_logz=True also evaluates the log-partition in the SAME
         pass over the score tensor (BACKWARD direction only, where both tables walk the triangle alike)."""
         T, N = _check_inputs(self.score, self.noiseScore)
-        s, z = _prep_score_for_sweep(self.score), _prep(self.noiseScore)
         direction = FORWARD if forward else BACKWARD
-        flags = SWEEP_VITERBI | (SWEEP_LOGSUM if with_logz else 0)
-        code, _, lse, ws = sweep(s, z, direction, flags)
-        forced = _forced_tensor(forcedStartPos, N, T, s.device)
+        code, lse, ws = self._swept(direction, with_logz)
+        forced = _forced_tensor(forcedStartPos, N, T, code.device)
         pairs, counts = backtrack(code, forced, direction)
         logz = None
         if with_logz:
             logz = _poison_if_flagged(ws, lse[T - 1 if forward else 0].clone())
         self._last_ws = ws
         return pairs, counts, logz
+
+    def _swept(self, direction: int, with_logz: bool):
+        """The DP tables do not depend on forcedStartPos (only back-tracking does, reference :61-71): the sweep of an
+        object is run once per direction and reused by later decode() calls -- the segment loop of the model decodes
+        every segment of a batch with a different forced start (transkun_b200.batched).  Keyed by the tensors'
+        version counters, so an in-place update of score / noiseScore invalidates it."""
+        key = (direction, self.score.data_ptr(), self.score._version, self.noiseScore.data_ptr(), self.noiseScore._version)
+        cache = getattr(self, "_sweep_cache", None)
+        if cache is not None and cache[0] == key and (cache[2] is not None or not with_logz):
+            return cache[1], cache[2], cache[3]
+        s, z = _prep_score_for_sweep(self.score), _prep(self.noiseScore)
+        flags = SWEEP_VITERBI | (SWEEP_LOGSUM if with_logz else 0)
+        code, _, lse, ws = sweep(s, z, direction, flags)
+        self._sweep_cache = (key, code, lse, ws)
+        return code, lse, ws
 
     def _raise_if_timed_out(self):
         ws = getattr(self, "_last_ws", None)
