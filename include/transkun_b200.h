@@ -209,6 +209,17 @@ int tkb_sip_score_scaled(const float *q, const float *k, const float *diag, int 
                          float *out_score, int64_t pitch, void *stream);
 
 /*
+ * Adjoint of the scorer's epilogue (training): from grad_score = dL/dS, [T][T][pitch] fp32 (track innermost, what
+ * tkb_semicrf_marginals writes), produce in one pass
+ *     out_gl   [n_tracks][T][T]: Gl[n][e][b] = grad_score[e][b][n] * scale * (e-b) for b < e, else 0
+ *     out_gdiag[n_tracks][T]   : grad_score[e][e][n]
+ * so that dq[n] = Gl[n] @ k[n] and dk[n] = Gl[n]^T @ q[n] are two plain batched library GEMMs
+ * (autograd of LayersTransformer.py:410-440).
+ */
+int tkb_sip_backward_prep(const float *grad_score, int64_t pitch, int n_tracks, int T, float scale, float *out_gl,
+                          float *out_gdiag, void *stream);
+
+/*
  * STFT / log-mel frontend.  Replaces Util.py:104-113 (Spectrum.forward) and :156-167
  * (MelSpectrum.forward with log=True): for every frame, audio channel and window
  *     X = rfft(frame * window, norm="ortho");  P = |X|^2;  (to_mono: mean over channels)

@@ -8,7 +8,7 @@ loss = -logp.sum(-1).mean(); (loss/50).backward()).
     NVLink (NCCL) so that every rank holds the full d ctx for the (replicated) backbone, and the scorer's weight gradients
     are all-reduced.
 The reference trains with --allow_tf32 (train.py:41-43): the scorer runs its one-pass TF32 mode here.
-Rank 0 prints one JSON line: ms per step (CUDA events, max over ranks), cells/s (T^2 * B * P per step), and the share of
+Rank 0 prints one JSON line: ms per step (CUDA events, median over the steps, max over ranks), cells/s (T^2 * B * P per step), and the share of
 the semi-CRF part against its HBM roofline (4N[3T(T+1)/2 + T^2] bytes per step).
 usage: [torchrun ...] python scripts/config4_train.py [--steps 10]"""
 import argparse
@@ -28,7 +28,7 @@ from transkun_b200.LayersTransformer import ScaledInnerProductIntervalScorer  # 
 from transkun_b200.sharded import track_shard  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--B", type=int, default=4)
 ap.add_argument("--T", type=int, default=691)
 args = ap.parse_args()
@@ -90,14 +90,16 @@ t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 t0.record(stream)
 for _ in range(args.steps):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    loss = step(ev)
+    loss = float(step(ev))
     parts.append(ev)
 t1.record(stream)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize(dev)
-ms = t0.elapsed_time(t1) / args.steps
-seg = [sum(e[i].elapsed_time(e[i + 1]) for e in parts) / len(parts) for i in range(4)]
+import statistics
+# median over the steps: the step is short enough (a few ms) for host scheduling noise to show up in single steps
+ms = statistics.median(e[0].elapsed_time(e[4]) for e in parts)
+seg = [statistics.median(e[i].elapsed_time(e[i + 1]) for e in parts) for i in range(4)]
 tt = torch.tensor([ms] + seg, device=dev)
 if world > 1:
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -114,7 +116,7 @@ if rank == 0:
         "config": f"training step: ctx[{B},{P},{T},{D}] -> scorer -> CRF.logProb -> backward, symbols sharded over {world} GPU(s)",
         "n_gpus": world, "steps": args.steps, "ms_per_step": ms, "cells_per_s": float(T) * T * B * P / (ms * 1e-3),
         "parts_ms": {"scorer_forward": seg[0], "logProb_forward": seg[1], "backward": seg[2], "exchange": seg[3]},
-        "loss": float(loss),
+        "loss": loss,
         "semicrf_roofline": {"algorithmic_bytes_busiest_rank": alg, "forward_plus_backward_ms": crf_ms,
                              "GBps": alg / (crf_ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (crf_ms * 1e-3) / 1e9 / peak,
                              "note": "backward also contains the scorer adjoint (torch.bmm), so this understates the CRF kernels"},

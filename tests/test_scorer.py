@@ -3,6 +3,7 @@ kernel vs the oracle (GPU, through the C ABI).  Tolerance: the kernel multiplies
 mantissa, the reference's --allow_tf32 regime) and accumulates in fp32: |err| <= 2e-3 * max|S| per case;
 inputs that TF32 represents exactly (small integers) must come out bit-exact."""
 import glob
+import math
 import os
 
 import numpy as np
@@ -69,7 +70,7 @@ def test_kernel_precise_mode_is_fp32_grade(NT, T, D):
     scale = want[tri].abs().max().item()
     err_p = (sip_score(q.cuda(), k.cuda(), diag.cuda(), precise=True).cpu().double() - want)[tri].abs().max().item()
     err_1 = (sip_score(q.cuda(), k.cuda(), diag.cuda(), precise=False).cpu().double() - want)[tri].abs().max().item()
-    assert err_p <= 3e-6 * scale, (err_p, scale)
+    assert err_p <= 3e-5 * scale, (err_p, scale)
     assert err_1 <= 2e-3 * scale and err_1 > 10 * err_p
 
 
@@ -121,20 +122,26 @@ def test_kernel_random_inputs_and_crf_roundtrip():
 
 
 @pytest.mark.gpu
-def test_scorer_backward_matches_torch_formula():
+@pytest.mark.parametrize("B,P,T,D", [(1, 4, 50, 64), (2, 45, 70, 256), (1, 33, 97, 32)])
+def test_scorer_backward_matches_torch_formula(B, P, T, D):
+    """Gradients w.r.t. ctx and the projection weights through the kernel pair (forward tcgen05, backward
+    tkb_sip_backward_prep + two library GEMMs) against autograd of the reference's formula; the upstream gradient is
+    dense (non-zero above the diagonal too: those outputs are constants, their gradient must be ignored)."""
     from transkun_b200.LayersTransformer import ScaledInnerProductIntervalScorer
     torch.manual_seed(1)
-    m = ScaledInnerProductIntervalScorer(64, 1).cuda()
-    ctx = torch.randn(1, 4, 50, 64, device="cuda", requires_grad=True)
+    m = ScaledInnerProductIntervalScorer(D, 1).cuda()
+    ctx = torch.randn(B, P, T, D, device="cuda", requires_grad=True)
     S, _ = m(ctx)
-    w = torch.randn_like(S).tril_() if False else torch.randn_like(S)
-    tri = torch.tril(torch.ones(50, 50, device="cuda"))[:, :, None, None]
-    (S * w * tri).sum().backward()
-    g1 = ctx.grad.clone()
+    w = torch.randn_like(S)
+    tri = torch.tril(torch.ones(T, T, device="cuda"))[:, :, None, None]
+    (S * w).sum().backward()
+    g1, gw1 = ctx.grad.clone(), m.map[0].weight.grad.clone()
     ctx.grad = None
+    m.zero_grad()
     y = m.map(ctx)
-    q, k, d = y[..., :64] / 8.0, y[..., 64:128], y[..., 128]
-    t = torch.arange(50, device="cuda", dtype=torch.float32)
+    q, k, d = y[..., :D] / math.sqrt(D), y[..., D:2 * D], y[..., 2 * D]
+    t = torch.arange(T, device="cuda", dtype=torch.float32)
     S2 = torch.einsum("iped,ipbd->ipeb", q, k) * (t[:, None] - t[None, :]).abs() + torch.diag_embed(d)
     (S2.permute(2, 3, 0, 1) * w * tri).sum().backward()
-    torch.testing.assert_close(g1, ctx.grad, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(g1, ctx.grad, rtol=2e-3, atol=2e-3 * float(ctx.grad.abs().max()))
+    torch.testing.assert_close(gw1, m.map[0].weight.grad, rtol=2e-3, atol=2e-3 * float(gw1.abs().max()))
