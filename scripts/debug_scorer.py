@@ -1,38 +1,31 @@
-"""GPU diagnostics for the tcgen05 scorer: exact-integer inputs, prints where the output differs."""
+"""Scorer timing (CUDA events): one-pass TF32 and 3xTF32, at the benchmark shape and the model shape; TKB_SCORER_GQ selects the
+block-order group size (quads of 4 tracks whose tiles run back to back).  usage: python scripts/debug_scorer.py"""
 import sys
-import time
 import torch
 sys.path.insert(0, ".")
 from transkun_b200.LayersTransformer import sip_score
 
-def run(NT, T, D, seed=0, timing=False):
-    g = torch.Generator().manual_seed(seed)
-    q = torch.randint(-3, 4, (NT, T, D), generator=g).float()
-    k = torch.randint(-3, 4, (NT, T, D), generator=g).float()
-    diag = torch.randn(NT, T, generator=g)
-    qc, kc, dc = q.cuda(), k.cuda(), diag.cuda()
-    S = sip_score(qc, kc, dc)
-    torch.cuda.synchronize()
-    t = torch.arange(T, dtype=torch.float32)
-    want = (torch.einsum("ned,nbd->neb", q, k) / (D ** 0.5)) * (t[:, None] - t[None, :]).abs()
-    want = (want + torch.diag_embed(diag)).permute(1, 2, 0)
-    tri = torch.tril(torch.ones(T, T, dtype=torch.bool))
-    bad = ((S.cpu() != want) & tri[:, :, None])
-    msg = f"NT={NT} T={T} D={D}: bad {int(bad.sum())} / {int(tri.sum()) * NT}"
-    if bad.any():
-        idx = bad.nonzero()
-        e, b, n = idx[0].tolist()
-        msg += f" first (e={e},b={b},n={n}) got {float(S[e,b,n])} want {float(want[e,b,n])}; bad e range {int(idx[:,0].min())}-{int(idx[:,0].max())} b range {int(idx[:,1].min())}-{int(idx[:,1].max())} tracks {sorted(set(idx[:,2].tolist()))[:10]}"
-    if timing:
-        for _ in range(3): sip_score(qc, kc, dc, out=S)
-        torch.cuda.synchronize(); t0 = time.time()
-        for _ in range(10): sip_score(qc, kc, dc, out=S)
-        torch.cuda.synchronize(); dt = (time.time() - t0) / 10
-        ob = 4 * NT * T * (T + 1) / 2
-        msg += f" | {dt*1e6:.0f} us, out {ob/dt/1e9:.0f} GB/s, {2*D*NT*T*(T+1)/2/dt/1e12:.1f} TFLOP/s"
-    print(("OK   " if not bad.any() else "FAIL ") + msg, flush=True)
 
-if __name__ == "__main__":
-    for a in [(8, 64, 32), (8, 128, 32), (8, 128, 256), (8, 200, 256), (3, 70, 64), (16, 257, 256), (90, 691, 256)]:
-        run(*a)
-    run(88, 2048, 256, timing=True)
+def run(NT, T, D, precise):
+    g = torch.Generator().manual_seed(0)
+    q, k, d = torch.randn(NT, T, D, generator=g).cuda(), torch.randn(NT, T, D, generator=g).cuda(), torch.randn(NT, T, generator=g).cuda()
+    P = (NT + 3) // 4 * 4
+    S = torch.empty((T, T, P), device="cuda")[:, :, :NT]
+    for _ in range(3):
+        sip_score(q, k, d, out=S, precise=precise)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        sip_score(q, k, d, out=S, precise=precise)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    out_bytes = 4.0 * NT * T * (T + 1) / 2
+    flops = 2.0 * D * (3 if precise else 1) * NT * T * (T + 1) / 2
+    print(f"NT={NT} T={T} D={D} {'3xTF32' if precise else 'TF32  '}: {us:7.0f} us  {out_bytes / us / 1e3:6.0f} GB/s of output  {flops / us / 1e6:6.1f} TFLOP/s"
+          f"  (incl. operand split/concat on the host side for 3xTF32)", flush=True)
+
+
+for NT, T in ((88, 2048), (90, 691), (360, 691)):
+    for precise in (False, True):
+        run(NT, T, 256, precise)

@@ -18,6 +18,8 @@
 // length factor, the diagonal and the triangle mask, 16-byte stores [e][b][4 tracks].
 //
 // Precision: TF32 operands (the reference's own --allow_tf32 regime, train.py:41-43), fp32 accumulate.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tkb {
@@ -96,7 +98,8 @@ struct ScorerParams {
     long long pitch;
     int NT, T, D;
     float qscale;               // 1/sqrt(D)
-    int tiles_b_total;          // helper for tile decoding
+    int tiles_b_total;          // tiles of the lower triangle
+    int gq;                     // track quads per block-order group
 };
 
 // tile index -> (eb, bb): lower-triangular enumeration; row eb has nb_row(eb) = min(ceil(T/64), 2*eb + 2) tiles
@@ -109,16 +112,22 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sip_scorer_kernel(const ScorerP
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = p.T, D = p.D, NT = p.NT;
-    // track quads are the fastest-varying block index: the CTAs that write the two 16-byte halves of a 32-byte
-    // sector (and all 22 quads of a tile) are dispatched together, so L2 sees whole sectors before it evicts them
+    // Block order: (group of p.gq track quads) > tile > quad in the group; p.gq = all quads by default, i.e. the CTAs of all
+    // 22 quads of a tile are dispatched together and L2 assembles whole 352-byte cells / 128-byte lines of the
+    // track-innermost output before it evicts them.  Measured round 2 (scripts/debug_scorer.py, TKB_SCORER_GQ): running
+    // all tiles of 2 / 4 / 8 quads back to back keeps their q / k rows in L2 (the operands are no longer streamed from
+    // DRAM 4.8 times) but is SLOWER -- 1294 / 1045 / 910 us against 835 us at T=2048 -- because the output then reaches
+    // DRAM as isolated 32-byte sectors.  The kernel is bound by how its stores assemble, not by operand traffic.
     const int ngq = (NT + SC_NG - 1) / SC_NG;
-    const int g = (int)blockIdx.x % ngq;
+    const int gq = p.gq;
+    const int g = ((int)blockIdx.x / (p.tiles_b_total * gq)) * gq + (int)blockIdx.x % gq;
+    if (g >= ngq) return;   // the last group may be short (whole CTA: nothing allocated yet)
     const int n0 = g * SC_NG;
     // decode (eb, bb) from blockIdx.x
     const int nbb = (T + SC_TB - 1) / SC_TB;
     int eb = 0, bb = 0;
     {
-        int rem = (int)blockIdx.x / ngq;
+        int rem = ((int)blockIdx.x / gq) % p.tiles_b_total;
         for (;;) {
             const int row = min(nbb, 2 * eb + 2);
             if (rem < row) {
@@ -303,7 +312,15 @@ extern "C" int tkb_sip_score_scaled(const float *q, const float *k, const float 
     long long tiles = 0;
     for (int eb = 0; eb < neb; ++eb) tiles += (2 * eb + 2 < nbb) ? 2 * eb + 2 : nbb;
     p.tiles_b_total = (int)tiles;
-    dim3 grid((unsigned)(tiles * ((n_tracks + SC_NG - 1) / SC_NG)));
+    const int ngq = (n_tracks + SC_NG - 1) / SC_NG;
+    static int gq_env = -1;
+    if (gq_env < 0) {
+        const char *e = getenv("TKB_SCORER_GQ");   // diagnostics: quads per block-order group (default: all)
+        gq_env = e ? atoi(e) : 0;
+    }
+    p.gq = gq_env > 0 ? gq_env : ngq;
+    if (p.gq > ngq) p.gq = ngq;
+    dim3 grid((unsigned)(tiles * p.gq * ((ngq + p.gq - 1) / p.gq)));
     sip_scorer_kernel<<<grid, SC_THREADS, kScorerSmem, (cudaStream_t)stream_>>>(p);
     TKB_CUDA(cudaGetLastError());
     return 0;
