@@ -1,5 +1,5 @@
-"""Scorer timing (CUDA events): one-pass TF32 and 3xTF32, at the benchmark shape and the model shape; TKB_SCORER_GQ selects the
-block-order group size (quads of 4 tracks whose tiles run back to back).  usage: python scripts/debug_scorer.py"""
+"""Scorer timing (CUDA events): one-pass TF32 and 3xTF32, at the benchmark shape and the model shape; TKB_SCORER_CX (cluster width 1/2/4:
+CTAs sharing one multicast q tile) and TKB_SCORER_BAND (tile rows per band of the block order) select the variants.  usage: python scripts/debug_scorer.py"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -9,7 +9,7 @@ from transkun_b200.LayersTransformer import sip_score
 def run(NT, T, D, precise):
     g = torch.Generator().manual_seed(0)
     q, k, d = torch.randn(NT, T, D, generator=g).cuda(), torch.randn(NT, T, D, generator=g).cuda(), torch.randn(NT, T, generator=g).cuda()
-    P = (NT + 3) // 4 * 4
+    P = (NT + 7) // 8 * 8
     S = torch.empty((T, T, P), device="cuda")[:, :, :NT]
     for _ in range(3):
         sip_score(q, k, d, out=S, precise=precise)

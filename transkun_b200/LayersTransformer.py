@@ -42,8 +42,9 @@ def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.T
     """q, k: [NT, T, D] fp32 CUDA contiguous; diag: [NT, T].  Returns score [T, T, NT] (lower triangle; zeros above).
     precise=None follows the reference's switch: 3xTF32 unless torch.backends.cuda.matmul.allow_tf32 is set.
 
-    When NT is not a multiple of 4 (the model: 90 symbols) the result is a [T, T, NT] view of a buffer whose track
-    axis is padded to a multiple of 4 (strides (T*P, P, 1)): the semi-CRF sweep then keeps its 16-byte copy path
+    When NT is not a multiple of 8 (the model: 90 symbols) the result is a [T, T, NT] view of a buffer whose track
+    axis is padded to a multiple of 8 (strides (T*P, P, 1)): every cell then starts on a 32-byte sector, which the
+    scorer writes whole (8 tracks per store), and the semi-CRF sweep keeps its 16-byte / TMA copy path
     (tkb_semicrf_sweep_pitched) instead of the 8-byte one a dense [T, T, 90] tensor forces."""
     if not (q.is_cuda and k.is_cuda and diag.is_cuda):
         raise RuntimeError("transkun_b200 has no CPU path: scorer inputs must be CUDA tensors")
@@ -53,7 +54,7 @@ def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.T
     if precise is None:
         precise = not torch.backends.cuda.matmul.allow_tf32
     if out is None:
-        P = (NT + 3) // 4 * 4
+        P = (NT + 7) // 8 * 8
         out = torch.zeros((T, T, P), dtype=torch.float32, device=q.device)[:, :, :NT]
     assert out.shape == (T, T, NT) and out.stride(2) == 1 and out.stride(0) == T * out.stride(1)
     scale = 1.0 / math.sqrt(D)
