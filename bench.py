@@ -19,6 +19,10 @@ cpu_baseline / --impl reference : the reference's OWN PyTorch-CPU path -- the un
            baseline/_ref (baseline/ref_loader.py): NeuralSemiCRFInterval(score, noise).computeLogZ(noBackward=True) +
            .decode() on all host cores (kind "reference").  Only if baseline/_ref is absent does it fall back to the
            C/OpenMP oracle port (kind "port", ~16x faster than the reference on the same CPU).
+scorer   : (1 GPU) the interval scorer in front of the same step, q, k [N, T, 256] -> score -> logZ + decode: time of
+           tkb_sip_score in both precision modes, of the chain, and GB/s of its algorithmic bytes (output written
+           once + operands read once) against the same HBM peak.  --workload scorer+crf makes that chain the timed step
+           (roofline block = the scorer kernel; e2e uploads q / k / diag instead of the score tensor).
 Multi-GPU: tracks shard with no data-path collective (weak scaling: every rank owns its own 88 tracks); the only
            exchange is the all-gather of the packed intervals: copy-engine pushes into symmetric NVLink peer memory on a
            side stream, overlapped with the next step's sweep (transkun_b200.sharded.PushGather; NCCL all-gather
@@ -55,6 +59,11 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tsweep", action="store_true", help="add a T sweep 256..4096 (config 5) to the JSON line")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other-shapes and scorer blocks (clean ncu launch lists)")
+    ap.add_argument("--workload", default="crf", choices=["crf", "scorer+crf"],
+                    help="crf: BASELINE.json's metric, score[T,T,N] resident (default).  scorer+crf: the same step fed from "
+                         "the scorer's operands q, k [N,T,256] (tkb_sip_score -> sweep -> back-track), roofline block = "
+                         "the scorer kernel, e2e uploads q/k/diag instead of the score tensor")
     return ap.parse_args()
 
 
@@ -78,9 +87,9 @@ def peak_hbm():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)"
 
 
-def ncu_traffic(T, N):
-    """DRAM bytes per sweep launch from the committed ncu --set full capture of this workload, if any."""
-    path = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+def ncu_traffic(T, N, name="sweep_traffic.json"):
+    """DRAM bytes per launch of the kernel from the committed ncu --set full capture of this workload, if any."""
+    path = os.path.join(ROOT, "profiles", name)
     try:
         rec = json.load(open(path))
         if rec.get("T") == T and rec.get("N") == N:
@@ -290,7 +299,27 @@ def run_ours(args):
         if int(agree.item()) == 0:
             push = fused = None
 
+    with_scorer = args.workload == "scorer+crf"
+    ev_scorer = []
+    D_MODEL = 256
+    if with_scorer:
+        from transkun_b200.LayersTransformer import sip_score
+        gq = torch.Generator().manual_seed(4321 + rank)
+        q_pin = torch.randn((n_local, T, D_MODEL), generator=gq).pin_memory()
+        k_pin = torch.randn((n_local, T, D_MODEL), generator=gq).pin_memory()
+        dg_pin = torch.randn((n_local, T), generator=gq).pin_memory()
+        q_d, k_d, dg_d = q_pin.to(dev), k_pin.to(dev), dg_pin.to(dev)
+        score.zero_()  # the scorer writes end >= begin; the rest of the buffer is defined as zero
+
     def step(record=False):
+        if with_scorer:  # one-pass TF32: the regime the reference trains in (train.py:41-43)
+            if record:
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(stream)
+            sip_score(q_d, k_d, dg_d, out=score, precise=False)
+            if record:
+                s1.record(stream)
+                ev_scorer.append((s0, s1))
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -368,14 +397,21 @@ def run_ours(args):
     fence()
     e2e_steps = max(1, args.e2e_steps)
     d2h_bytes = 0
+    def e2e_crf():
+        if with_scorer:  # HOST q, k, diag, noise -> scorer -> semi-CRF -> the reference's Python lists
+            qd, kd, dgd = q_pin.to(dev, non_blocking=True), k_pin.to(dev, non_blocking=True), dg_pin.to(dev, non_blocking=True)
+            sip_score(qd, kd, dgd, out=score, precise=False)
+            return NeuralSemiCRFInterval(score, noise_pin.to(dev, non_blocking=True))
+        # public API from HOST tensors: uploads the part of the score tensor the semi-CRF reads (end >= begin)
+        return NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev)
+
     with torch.no_grad():  # one untimed pass: first-use allocations of the e2e path
-        NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev).decodeWithLogZ()
+        e2e_crf().decodeWithLogZ()
     torch.cuda.synchronize(dev)
     tw0 = time.perf_counter()
     for _ in range(e2e_steps):
         with torch.no_grad():
-            # public API from HOST tensors: uploads the part of the score tensor the semi-CRF reads (end >= begin)
-            crf = NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev)
+            crf = e2e_crf()
             dec, logz = crf.decodeWithLogZ()
             logz_h = logz.cpu()
         maxc = max((len(d) for d in dec), default=0)
@@ -387,7 +423,7 @@ def run_ours(args):
     with torch.no_grad():
         torch.cuda.synchronize(dev)
         t_a = time.perf_counter()
-        crf = NeuralSemiCRFInterval.fromHost(score_pin, noise_pin, dev)
+        crf = e2e_crf()  # scorer+crf: includes the scorer launch
         torch.cuda.synchronize(dev)
         t_b = time.perf_counter()
         pairs_d, counts_d, logz_d = crf.decode_packed(None, False, with_logz=True)
@@ -410,6 +446,8 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_sec = float(tmax.item())
     h2d_bytes = NeuralSemiCRFInterval.lowerTriangleUploadBytes(T, n_local) + noise_pin.numel() * 4
+    if with_scorer:
+        h2d_bytes = (q_pin.numel() + k_pin.numel() + dg_pin.numel() + noise_pin.numel()) * 4
 
     # ---- other shapes of the same kernel (device-generated inputs; CUDA events) -------------------------------
     def time_shape(Ts, Ns, pad_to=None, reps=10):
@@ -430,11 +468,52 @@ def run_ours(args):
         del buf, sc, nz
         return {"T": Ts, "N": Ns, "track_pitch": P, "sweep_us": us, "GBps": gbs, "cells_per_s": float(Ts) * Ts * Ns / us * 1e6}
 
+    # ---- the interval scorer (tkb_sip_score) in front of the same sweep: q, k [N, T, 256] -> score -> logZ + decode ----
+    def time_scorer(Ts, Ns, reps=10):
+        from transkun_b200.LayersTransformer import sip_score as score_fn
+        P = (Ns + 7) // 8 * 8
+        gsc = torch.Generator(device=dev).manual_seed(99)
+        qs = torch.randn((Ns, Ts, D_MODEL), device=dev, generator=gsc)
+        ks = torch.randn((Ns, Ts, D_MODEL), device=dev, generator=gsc)
+        ds = torch.randn((Ns, Ts), device=dev, generator=gsc)
+        nz = torch.randn((Ts - 1, Ns), device=dev, generator=gsc)
+        sc = torch.zeros((Ts, Ts, P), device=dev)[:, :, :Ns]
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) * 1e3 / reps
+
+        def chain():
+            score_fn(qs, ks, ds, out=sc, precise=False)
+            code, _, lse, _ = sweep(sc, nz, BACKWARD, SWEEP_VITERBI | SWEEP_LOGSUM)
+            backtrack_records(code, None, BACKWARD, lse[0])
+
+        one = timed(lambda: score_fn(qs, ks, ds, out=sc, precise=False))
+        three = timed(lambda: score_fn(qs, ks, ds, out=sc, precise=True))
+        both = timed(chain)
+        alg = 4.0 * Ns * Ts * (Ts + 1) / 2.0 + 2.0 * Ns * Ts * D_MODEL * 4.0   # output written once + operands read once
+        del qs, ks, ds, nz, sc
+        return {"T": Ts, "N": Ns, "D": D_MODEL, "track_pitch": P, "scorer_tf32_us": one, "scorer_3xtf32_us": three,
+                "scorer_plus_crf_us": both, "cells_per_s_from_qk": float(Ts) * Ts * Ns / both * 1e6,
+                "algorithmic_bytes": alg, "GBps": alg / one / 1e3,
+                "note": "3xtf32 includes the operand split (tkb_sip_split3); scorer_plus_crf = tf32 scorer + fused sweep + "
+                        "back-track, CUDA events"}
+
     shapes = None
-    if world == 1:
+    scorer_shapes = None
+    if world == 1 and not args.no_extras:
         del score, noise
         torch.cuda.empty_cache()
-        shapes = [time_shape(691, 90, pad_to=92), time_shape(1024, 88)]
+        scorer_shapes = [time_scorer(T, n_local), time_scorer(691, 90)]
+        torch.cuda.empty_cache()
+        shapes = [time_shape(691, 90, pad_to=96), time_shape(1024, 88)]
         if args.tsweep:
             shapes += [time_shape(t_, 88, reps=5) for t_ in (256, 512, 2048, 4096)]
 
@@ -443,13 +522,26 @@ def run_ours(args):
         alg_bytes = 4.0 * n_local * T * (T + 1) / 2.0
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
         traffic = ncu_traffic(T, n_local)
-        for sh in shapes or []:
+        for sh in (shapes or []) + (scorer_shapes or []):
             sh["frac_of_hbm_peak"] = sh["GBps"] / peak
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "tkb::sweep_kernel<BACKWARD, A16, VITERBI|LOGSUM>",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sweep_ms, "peak_source": peak_src}
+        if with_scorer:  # the scorer kernel dominates this workload: output written once + operands read once
+            sc_ms = statistics.mean(a.elapsed_time(b) for a, b in ev_scorer)
+            sc_bytes = alg_bytes + 2.0 * n_local * T * D_MODEL * 4.0
+            roof = {"bound": "hbm", "achieved": sc_bytes / (sc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": sc_bytes / (sc_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(T, n_local, "scorer_traffic.json"),
+                    "kernel": "tkb::sip_scorer_kernel",
+                    "algorithmic_bytes_per_launch": sc_bytes, "kernel_ms": sc_ms, "peak_source": peak_src,
+                    "sweep": {"achieved": achieved, "frac": achieved / peak, "kernel_ms": sweep_ms}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(T, n_local, n_total, world),
+            "config": (dict(workload_config(T, n_local, n_total, world), workload_variant="scorer+crf: each step computes "
+                            "score[T,T,N] from q, k [N,T,256] fp32 randn (tkb_sip_score, one TF32 pass) before the semi-CRF step")
+                       if with_scorer else workload_config(T, n_local, n_total, world)),
             "exchange": ("none" if world == 1 else (
                 "fused: the back-track kernel stores every record into all ranks' symmetric (NVLink peer) buffers and "
                 "publishes a step flag" if fused is not None else (
@@ -457,14 +549,15 @@ def run_ours(args):
                     else "NCCL all-gather per step"))),
             "e2e": {"value": cells_per_step / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3, "breakdown": bd,
-                    "api": "NeuralSemiCRFInterval.fromHost(score, noise, device).decodeWithLogZ() from pinned host tensors "
-                           "(uploads the lower-triangle staircase of score, the part the semi-CRF reads); returns the "
-                           "reference's Python interval lists + logZ"},
-            "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "tkb::sweep_kernel<BACKWARD, A16, VITERBI|LOGSUM>",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sweep_ms, "peak_source": peak_src},
+                    "api": ("sip_score(q, k, diag from pinned host tensors) -> NeuralSemiCRFInterval(score, noise).decodeWithLogZ(); "
+                            "returns the reference's Python interval lists + logZ" if with_scorer else
+                            "NeuralSemiCRFInterval.fromHost(score, noise, device).decodeWithLogZ() from pinned host tensors "
+                            "(uploads the lower-triangle staircase of score, the part the semi-CRF reads); returns the "
+                            "reference's Python interval lists + logZ")},
+            "gpu_launches": (3 if with_scorer else 2) * args.steps,
+            "roofline": roof,
             "other_shapes": shapes,
+            "scorer": scorer_shapes,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

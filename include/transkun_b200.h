@@ -209,6 +209,13 @@ int tkb_sip_score_scaled(const float *q, const float *k, const float *diag, int 
                          float *out_score, int64_t pitch, void *stream);
 
 /*
+ * The operand split of the 3xTF32 mode in one pass: q, k [rows][D] fp32 -> q3 = [q_hi | q_hi | q_lo],
+ * k3 = [k_hi | k_lo | k_hi], each [rows][3 D], where x_hi is x with the 13 low mantissa bits cleared (exact in TF32)
+ * and x_lo = x - x_hi (exact in fp32).  D a multiple of 4, pointers 16-byte aligned.
+ */
+int tkb_sip_split3(const float *q, const float *k, long long rows, int D, float *q3, float *k3, void *stream);
+
+/*
  * Adjoint of the scorer's epilogue (training): from grad_score = dL/dS, [T][T][pitch] fp32 (track innermost, what
  * tkb_semicrf_marginals writes), produce in one pass
  *     out_gl   [n_tracks][T][T]: Gl[n][e][b] = grad_score[e][b][n] * scale * (e-b) for b < e, else 0

@@ -4,6 +4,9 @@
 //             as a function of N in {32, 64, 128, 256}, one and two CTAs per SM issuing at the same time.
 //  B. ingest: how many bytes per second can every SM pull through TMA 2-D tile copies ({32 floats, R rows} boxes,
 //             SWIZZLE_128B) out of an L2-resident operand, 2 CTAs per SM, 4 boxes in flight per CTA?
+//  C. scatter: writing [e][b][8 tracks] cells (32-byte pieces, 352 bytes apart) of a track-innermost [T][T][88] tensor:
+//             256-bit stores by 8 warps (one cell per lane) against TMA tensor stores of {8 tracks, B begins, 8 ends}
+//             boxes staged in shared memory.
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o umma_rate umma_rate.cu
 #include <cstdio>
@@ -182,6 +185,71 @@ static void run_ingest(EncodeTiledFn enc, float *buf, int rows, int sms, int cta
            ctas_per_sm, (int)((size_t)rows * 1024 >> 20), bytes / ms / 1e9, bytes / ms / 1e6 / sms);
 }
 
+// ---- C
+template <int BEGINS>
+__global__ void __launch_bounds__(256, 1) scatter_tma(const __grid_constant__ CUtensorMap map, int T, int iters) {
+    extern __shared__ unsigned char raw[];
+    const unsigned base = (smem_u32(raw) + 127u) & ~127u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kBoxBytes = 8 * BEGINS * 8 * 4;
+    constexpr int kIssuers = 128 / BEGINS * 8;   // BEGINS = 32: every warp issues its own boxes; 128: two warps per 16 ends
+    for (int i = threadIdx.x; i < 65536 / 4; i += 256) reinterpret_cast<float *>(raw + (base - smem_u32(raw)))[i] = 1.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (lane == 0 && warp < kIssuers) {
+        unsigned seed = blockIdx.x * 9781u + warp * 131u + 7u;
+        for (int it = 0; it < iters; ++it) {
+            seed = seed * 1664525u + 1013904223u;
+            const int e0 = (int)((seed >> 8) % (unsigned)(T / 8)) * 8;
+            const int b0 = (int)((seed >> 3) % (unsigned)(T / BEGINS)) * BEGINS;
+            const int n0 = (int)(seed % 11u) * 8;
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map), "r"(n0), "r"(b0),
+                         "r"(e0), "r"(base + (unsigned)(warp % (65536 / kBoxBytes)) * kBoxBytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+__global__ void __launch_bounds__(256, 1) scatter_lsu(float *out, int T, int iters) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned seed = blockIdx.x * 9781u + warp * 131u + 7u;
+    for (int it = 0; it < iters; ++it) {
+        seed = seed * 1664525u + 1013904223u;
+        const int e0 = (int)((seed >> 8) % (unsigned)(T / 8)) * 8;
+        const int b0 = (int)((seed >> 3) % (unsigned)(T / 32)) * 32;
+        const int n0 = (int)(seed % 11u) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float *o = out + ((size_t)(e0 + j) * T + b0 + lane) * 88 + n0;
+            const float v = (float)it;
+            asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(o), "f"(v) : "memory");
+        }
+    }
+}
+
+// structured like the scorer's epilogue: work item = (tile of 128 begins x 64 ends, group of TRACKS tracks), group fastest,
+// items dealt round-robin to the SMs: the SMs complete whole cells / lines at about the same time
+template <int TRACKS>
+__global__ void __launch_bounds__(256, 1) scatter_tiles(float *out, int T, int items) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int G = 88 / TRACKS;          // groups per cell (88 tracks)
+    constexpr int LPC = TRACKS / 8;         // lanes per cell
+    const int q = warp & 3, h = warp >> 2;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int tile = w / G, g = w % G;
+        const int b0 = (tile % (T / 128)) * 128, e0 = (tile / (T / 128)) * 64 % T;
+        for (int j = 0; j < 32 * LPC; ++j) {   // a warp covers 32 begins x 32 ends; with LPC lanes per cell it takes LPC x more instructions
+            const int cell = (j * 32 + lane) / LPC, part = (j * 32 + lane) % LPC;
+            const int e = e0 + 32 * h + cell / 32, b = b0 + 32 * q + cell % 32;
+            float *o = out + ((size_t)e * T + b) * 88 + g * TRACKS + part * 8;
+            const float v = (float)w;
+            asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(o), "f"(v) : "memory");
+        }
+    }
+}
+
 int main() {
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
@@ -210,6 +278,83 @@ int main() {
         run_ingest<256, 3>(enc, buf, rows, sms, 2);
         run_ingest<128, 4>(enc, buf, rows, sms, 1);
         CK(cudaFree(buf));
+    }
+    {
+        const int T = 2048;
+        float *out;
+        CK(cudaMalloc(&out, (size_t)T * T * 88 * 4));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        float ms;
+        const int iters = 2048;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
+            scatter_lsu<<<sms, 256>>>(out, T, iters);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("scatter 32-byte cells, 256-bit stores, 8 warps/SM: %.1f GB/s per SM, %.2f TB/s total\n",
+               (double)iters * 8 * 8192 / ms / 1e6, (double)sms * iters * 8 * 8192 / ms / 1e9);
+        for (int begins : {32, 128}) {
+            CUtensorMap map;
+            const cuuint64_t dims[3] = {88, (cuuint64_t)T, (cuuint64_t)T};
+            const cuuint64_t strides[2] = {88 * 4, (cuuint64_t)T * 88 * 4};
+            const cuuint32_t box[3] = {8, (cuuint32_t)begins, 8};
+            const cuuint32_t es[3] = {1, 1, 1};
+            if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+                printf("encode failed\n");
+                return 1;
+            }
+            const size_t smem = 65536 + 128;
+            const int issuers = 128 / begins * 8 > 8 ? 8 : 128 / begins * 8;
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaEventRecord(e0));
+                if (begins == 32) {
+                    CK(cudaFuncSetAttribute(scatter_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    scatter_tma<32><<<sms, 256, smem>>>(map, T, iters);
+                } else {
+                    CK(cudaFuncSetAttribute(scatter_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    scatter_tma<128><<<sms, 256, smem>>>(map, T, iters / 4);
+                }
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double bytes = begins == 32 ? (double)iters * issuers * 8192 : (double)(iters / 4) * issuers * 32768;
+            printf("scatter 32-byte cells, TMA store boxes {8 tracks, %d begins, 8 ends}, %d issuing threads/SM: %.1f GB/s per SM, %.2f TB/s total\n",
+                   begins, issuers, bytes / ms / 1e6, sms * bytes / ms / 1e9);
+        }
+        {
+            const int tiles = (T / 128) * (T / 64) * 2;   // two sweeps over the tensor
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaEventRecord(e0));
+                scatter_tiles<8><<<sms, 256>>>(out, T, tiles * 11);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("tile-ordered 32-byte cells ( 8 tracks per item), 256-bit stores: %.2f TB/s total\n", (double)tiles * 11 * 128 * 64 * 32 / ms / 1e9);
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaEventRecord(e0));
+                scatter_tiles<16><<<sms, 256>>>(out, T, tiles * 5);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("tile-ordered 64-byte cells (16 tracks per item), 256-bit stores: %.2f TB/s total\n", (double)tiles * 5 * 128 * 64 * 64 / ms / 1e9);
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaEventRecord(e0));
+                scatter_tiles<88><<<sms, 256>>>(out, T, tiles);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("tile-ordered whole cells (88 tracks per item, contiguous), 256-bit stores: %.2f TB/s total\n", (double)tiles * 128 * 64 * 352 / ms / 1e9);
+        }
+        CK(cudaFree(out));
     }
     return 0;
 }

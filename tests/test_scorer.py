@@ -145,3 +145,21 @@ def test_scorer_backward_matches_torch_formula(B, P, T, D):
     (S2.permute(2, 3, 0, 1) * w * tri).sum().backward()
     torch.testing.assert_close(g1, ctx.grad, rtol=2e-3, atol=2e-3 * float(ctx.grad.abs().max()))
     torch.testing.assert_close(gw1, m.map[0].weight.grad, rtol=2e-3, atol=2e-3 * float(gw1.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,D", [(7, 32), (691, 256), (1000, 96)])
+def test_split3_matches_the_definition(rows, D):
+    """tkb_sip_split3 = [hi | hi | lo], [hi | lo | hi] with hi/lo of LayersTransformer._split_tf32, bit for bit."""
+    from transkun_b200 import _lib
+    from transkun_b200.LayersTransformer import _split_tf32
+    g = torch.Generator().manual_seed(rows)
+    q, k = torch.randn(rows, D, generator=g).cuda() * 3, torch.randn(rows, D, generator=g).cuda() * 0.01
+    q3, k3 = torch.empty(rows, 3 * D, device="cuda"), torch.empty(rows, 3 * D, device="cuda")
+    rc = _lib.load().tkb_sip_split3(q.data_ptr(), k.data_ptr(), rows, D, q3.data_ptr(), k3.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "tkb_sip_split3")
+    qh, ql = _split_tf32(q)
+    kh, kl = _split_tf32(k)
+    assert torch.equal(q3, torch.cat([qh, qh, ql], 1)) and torch.equal(k3, torch.cat([kh, kl, kh], 1))
+    assert torch.equal(qh + ql, q)

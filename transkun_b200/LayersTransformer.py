@@ -58,12 +58,13 @@ def sip_score(q: torch.Tensor, k: torch.Tensor, diag: torch.Tensor, out: torch.T
         out = torch.zeros((T, T, P), dtype=torch.float32, device=q.device)[:, :, :NT]
     assert out.shape == (T, T, NT) and out.stride(2) == 1 and out.stride(0) == T * out.stride(1)
     scale = 1.0 / math.sqrt(D)
-    if precise:
-        qh, ql = _split_tf32(q)
-        kh, kl = _split_tf32(k)
-        q = torch.cat([qh, qh, ql], dim=2)
-        k = torch.cat([kh, kl, kh], dim=2)
     with torch.cuda.device(q.device):
+        if precise:   # [q_hi, q_hi, q_lo] x [k_hi, k_lo, k_hi] (see _split_tf32), prepared by one kernel
+            q3, k3 = torch.empty((NT, T, 3 * D), device=q.device), torch.empty((NT, T, 3 * D), device=q.device)
+            rc = _lib.load().tkb_sip_split3(q.data_ptr(), k.data_ptr(), NT * T, D, q3.data_ptr(), k3.data_ptr(),
+                                            torch.cuda.current_stream(q.device).cuda_stream)
+            _lib.check(rc, "tkb_sip_split3")
+            q, k = q3, k3
         rc = _lib.load().tkb_sip_score_scaled(q.data_ptr(), k.data_ptr(), diag.data_ptr(), NT, T, q.shape[2], scale,
                                               out.data_ptr(), out.stride(1),
                                               torch.cuda.current_stream(q.device).cuda_stream)

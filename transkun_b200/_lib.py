@@ -21,7 +21,7 @@ EXPORTS = (
     "tkb_version", "tkb_last_error", "tkb_device_check", "tkb_sweep_workspace_bytes", "tkb_semicrf_sweep",
     "tkb_semicrf_sweep_pitched",
     "tkb_sweep_status", "tkb_semicrf_backtrack", "tkb_semicrf_backtrack_strided", "tkb_semicrf_backtrack_push", "tkb_wait_flags", "tkb_semicrf_marginals", "tkb_semicrf_evalpath",
-    "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_sip_score_pitched", "tkb_sip_score_scaled", "tkb_sip_backward_prep", "tkb_logmel_workspace_bytes", "tkb_logmel",
+    "tkb_semicrf_evalpath_grad", "tkb_sip_score", "tkb_sip_score_pitched", "tkb_sip_score_scaled", "tkb_sip_split3", "tkb_sip_backward_prep", "tkb_logmel_workspace_bytes", "tkb_logmel",
     "tkb_upload_lower_triangle",
 )
 
@@ -83,6 +83,8 @@ def load() -> ctypes.CDLL:
     L.tkb_sip_score_pitched.argtypes = [vp, vp, vp, i, i, i, vp, ctypes.c_int64, vp]
     L.tkb_sip_score_scaled.restype = i
     L.tkb_sip_score_scaled.argtypes = [vp, vp, vp, i, i, i, f, vp, ctypes.c_int64, vp]
+    L.tkb_sip_split3.restype = i
+    L.tkb_sip_split3.argtypes = [vp, vp, ctypes.c_longlong, i, vp, vp, vp]
     L.tkb_sip_backward_prep.restype = i
     L.tkb_sip_backward_prep.argtypes = [vp, ctypes.c_int64, i, i, f, vp, vp, vp]
     L.tkb_sip_score.restype = i
