@@ -4,7 +4,7 @@
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 mkdir -p gpurun_out
-timeout 300 $TR --master-port 29601 scripts/config5_sweep.py --steps 20 2>gpurun_out/mg_${N}_c5.err | tail -1 > gpurun_out/mg_${N}_config5.json
+[ -n "$SKIP_C5" ] || timeout 300 $TR --master-port 29601 scripts/config5_sweep.py --steps 20 2>gpurun_out/mg_${N}_c5.err | tail -1 > gpurun_out/mg_${N}_config5.json
 timeout 300 $TR --master-port 29602 scripts/config4_train.py --steps 30 2>gpurun_out/mg_${N}_c4.err | tail -1 > gpurun_out/mg_${N}_config4.json
 for mode in ${MODES:-fused push}; do
   TKB_GATHER=$mode timeout 300 $TR --master-port 29603 bench.py --gpus $N --steps 50 --warmup 5 2>gpurun_out/mg_${N}_weak_$mode.err | tail -1 > gpurun_out/mg_${N}_weak_$mode.json

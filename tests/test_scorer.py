@@ -163,3 +163,29 @@ def test_split3_matches_the_definition(rows, D):
     kh, kl = _split_tf32(k)
     assert torch.equal(q3, torch.cat([qh, qh, ql], 1)) and torch.equal(k3, torch.cat([kh, kl, kh], 1))
     assert torch.equal(qh + ql, q)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NT,T,D,pitch", [(1, 1, 32, 1), (1, 2, 32, 3), (2, 33, 64, 2), (7, 64, 32, 7), (13, 130, 96, 14),
+                                          (12, 65, 160, 12), (17, 200, 32, 20), (90, 129, 64, 96)])
+def test_kernel_edges_small_and_unaligned(NT, T, D, pitch):
+    """Shapes at the edges of the tiling: T below one tile, a last track group of 1..7 tracks, an odd number of K chunks
+    (the second chunk of the last TMA box is out of bounds and zero-filled), and track pitches that take the 4-, 16- and
+    32-byte store paths.  Integer inputs: bit-exact against the fp32 formula wherever 1/sqrt(D) is exact, and nothing is
+    written outside the lower triangle or outside the first NT tracks of a cell."""
+    from transkun_b200.LayersTransformer import sip_score
+    g = torch.Generator().manual_seed(NT * 131 + T)
+    q = torch.randint(-3, 4, (NT, T, D), generator=g).float()
+    k = torch.randint(-3, 4, (NT, T, D), generator=g).float()
+    diag = torch.randn(NT, T, generator=g)
+    buf = torch.full((T, T, pitch), 7.0, device="cuda")
+    S = sip_score(q.cuda(), k.cuda(), diag.cuda(), out=buf[:, :, :NT], precise=False)
+    assert S.data_ptr() == buf.data_ptr()
+    t = torch.arange(T, dtype=torch.float32)
+    want = (torch.einsum("ned,nbd->neb", q, k) / (D ** 0.5)) * (t[:, None] - t[None, :]).abs()
+    want = (want + torch.diag_embed(diag)).permute(1, 2, 0)
+    tri = torch.tril(torch.ones(T, T, dtype=torch.bool))
+    got = buf.cpu()
+    torch.testing.assert_close(got[:, :, :NT][tri], want[tri], rtol=1e-6, atol=1e-5)
+    assert (got[:, :, :NT][~tri] == 7.0).all(), "cells above the diagonal are not touched"
+    assert (got[:, :, NT:] == 7.0).all(), "padding tracks are not touched"
