@@ -5,10 +5,31 @@
  * score tensor (bench.py e2e.breakdown).  This does it in one C loop over the device's packed result.
  *
  *   pairs_to_lists(pairs: buffer int32 [N][stride][2], counts: buffer int32 [N], stride: int) -> list[list[tuple[int,int]]]
+ *
+ * Positions are small non-negative integers that repeat across tracks: the int objects for 0 .. kIntCache-1 are created
+ * once and shared (one allocation per interval -- the tuple -- instead of three, and nothing but reference counts to
+ * touch when the result is freed), exactly like CPython's own cache for -5 .. 256.
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <stdint.h>
+
+enum { kIntCache = 1 << 16 };
+static PyObject *int_cache[kIntCache];   /* lazily filled, lives as long as the module */
+
+static inline PyObject *position(long v) {
+    if (v >= 0 && v < kIntCache) {
+        PyObject *o = int_cache[v];
+        if (!o) {
+            o = PyLong_FromLong(v);
+            if (!o) return NULL;
+            int_cache[v] = o;   /* the cache keeps this reference */
+        }
+        Py_INCREF(o);
+        return o;
+    }
+    return PyLong_FromLong(v);
+}
 
 static PyObject *pairs_to_lists(PyObject *self, PyObject *args) {
     Py_buffer pb, cb;
@@ -38,7 +59,7 @@ static PyObject *pairs_to_lists(PyObject *self, PyObject *args) {
         PyList_SET_ITEM(out, t, lst);
         const int32_t *p = pairs + t * stride * 2;
         for (Py_ssize_t i = 0; i < c; ++i) {
-            PyObject *b = PyLong_FromLong(p[2 * i]), *e = PyLong_FromLong(p[2 * i + 1]);
+            PyObject *b = position(p[2 * i]), *e = position(p[2 * i + 1]);
             PyObject *tup = (b && e) ? PyTuple_New(2) : NULL;
             if (!tup) {
                 Py_XDECREF(b);
