@@ -110,8 +110,6 @@ struct ScorerParams {
     int tiles, gpass;           // tiles of the lower triangle; track groups per pass of the work order (see item_of)
     unsigned long long *trace;  // diagnostics build only (TKB_TIMELINE): [grid][16] globaltimer stamps / cycle counters
     int ablate;                 // diagnostics build only: 1 = no MMAs, 2 = no stores, 4 = q box only, 8 = k box only,
-                                // 16 = no evict-last hint on the k boxes, 32 = stores without evict-first,
-                                // 64 = producer never waits for a free stage, 128 = stages freed by a plain arrive,
                                 // 256 = no cycle counters
 };
 
@@ -270,17 +268,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
                         if (it % SC_PRODUCERS != me) continue;
                         const int slot = it % SC_STAGES;
                         const long long c0 = SC_CLOCK();
-                        if (it >= SC_STAGES && !SC_ABLATE(64)) mbar_wait(empty_b + 8 * slot, (unsigned)(((it / SC_STAGES) - 1) & 1));
+                        if (it >= SC_STAGES) mbar_wait(empty_b + 8 * slot, (unsigned)(((it / SC_STAGES) - 1) & 1));
                         const long long c1 = SC_CLOCK();
                         c_wait += c1 - c0;
                         const unsigned stage = smem_base + (unsigned)slot * SC_STAGE_BYTES;
                         mbar_arrive_expect_tx(full_b + 8 * slot, (unsigned)(SC_CH * ((SC_ABLATE(4) ? 0 : SC_A_BYTES) + (SC_ABLATE(8) ? 0 : SC_B_BYTES))));
                         // the k tile of a column serves every tile row below it: keep it in L2 in preference to the rest
                         if (!SC_ABLATE(4)) {
-                            if (SC_ABLATE(16))
-                                tma_load_3d(stage, &mapk, 0, row0 + b0, st * SC_CH, full_b + 8 * slot);
-                            else
-                                tma_load_3d_hint(stage, &mapk, 0, row0 + b0, st * SC_CH, full_b + 8 * slot, keep);
+                            tma_load_3d_hint(stage, &mapk, 0, row0 + b0, st * SC_CH, full_b + 8 * slot, keep);
                         }
                         if (!SC_ABLATE(8)) tma_load_3d(stage + SC_CH * SC_A_BYTES, &mapq, 0, row0 + e0, st * SC_CH, full_b + 8 * slot);
                         c_issue += SC_CLOCK() - c1;
@@ -332,10 +327,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
                             for (int kk = 0; kk < SC_KC / SC_UMMA_K; ++kk)  // +32 bytes along K inside the swizzle atom = +2 in the address field
                                 if (!SC_ABLATE(1)) umma_tf32(tmem_base + t * SC_TN, da + 2 * kk, db + 2 * kk, idesc, (st > 0 || c > 0 || kk > 0) ? 1u : 0u);
                         }
-                        if (SC_ABLATE(128))
-                            mbar_arrive1(empty_b + 8 * slot);
-                        else
-                            umma_commit(empty_b + 8 * slot);
+                        umma_commit(empty_b + 8 * slot);
                         c_issue += SC_CLOCK() - c1;
                     }
                     if (t == min(SC_NG / 2, ntrk) - 1) umma_commit(acc_full_b);
@@ -432,14 +424,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
                         float *o = p.out + ((size_t)e * T + b) * p.pitch + n0;
                         if (align == 32 && ntrk == SC_NG) {
                             // written once, read by a later kernel: first in line for eviction, the operands stay
-                            if (SC_ABLATE(32))
-                                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0]),
-                                             "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                                             : "memory");
-                            else
-                                asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o),
-                                             "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                                             : "memory");
+                            asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o),
+                                         "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                                         : "memory");
                         } else if (align >= 16 && ntrk >= 4) {
                             *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
                             if (ntrk == SC_NG) {
