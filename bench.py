@@ -248,13 +248,15 @@ def run_ours(args):
     from transkun_b200 import _lib
     from transkun_b200.CRF.NeuralSemiCRFInterval import NeuralSemiCRFInterval, backtrack_records, sweep
     from transkun_b200._lib import BACKWARD, SWEEP_LOGSUM, SWEEP_VITERBI
-    from transkun_b200.sharded import FusedPushGather, PushGather, gather_records, track_shard
+    from transkun_b200.sharded import FusedPushGather, PushGather, bind_to_gpu_numa_node, gather_records, track_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep this rank's pinned host buffers and its Python work on the GPU's own NUMA node
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("TKB_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().tkb_device_check(), "tkb_device_check")
@@ -558,6 +560,7 @@ def run_ours(args):
             "roofline": roof,
             "other_shapes": shapes,
             "scorer": scorer_shapes,
+            "numa_node_rank0": numa_node,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

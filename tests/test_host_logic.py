@@ -71,3 +71,30 @@ def test_packed_intervals_are_validated_once():
         PackedIntervals(torch.tensor([[-1, 2]]), torch.tensor([0, 1]))
     with pytest.raises(ValueError):
         PackedIntervals(torch.tensor([[1, 2]]), torch.tensor([0, 2]))      # offsets past the pairs
+
+
+def test_numa_binding_reads_the_topology(tmp_path, monkeypatch):
+    """bind_to_gpu_numa_node: PCI address of the device -> numa_node -> cpulist -> sched_setaffinity on the intersection
+    with the CPUs the process may use; unreadable topology or an empty intersection changes nothing."""
+    import os
+    import types
+    import torch
+    from transkun_b200 import sharded
+    assert sharded._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    mine = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text(f"{mine[0]}\n")
+    calls = []
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: calls.append(set(cpus)))
+    assert sharded.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) == 1 and calls == [{mine[0]}]
+    (node / "cpulist").write_text("100000\n")          # a node whose CPUs this process cannot use
+    assert sharded.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None and len(calls) == 1
+    (dev / "numa_node").write_text("-1\n")             # no NUMA information
+    assert sharded.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert sharded.bind_to_gpu_numa_node(0, sysfs=str(tmp_path / "nowhere")) is None

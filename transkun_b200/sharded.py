@@ -18,6 +18,38 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys") -> Optional[int]:
+    """One process per GPU: restrict the calling process to the CPUs of the NUMA node its GPU hangs off, BEFORE it
+    allocates pinned host buffers (first touch then places them on that node, so the rank's host<->device copies do not
+    cross the socket interconnect and do not share a memory controller with the other ranks' uploads).  Returns the node,
+    or None when the topology cannot be read or the node's CPUs are not available to the process (nothing is changed)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        addr = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", addr, "numa_node")).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")).read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (AttributeError, OSError, ValueError):
+        return None
+
+
 def track_shard(n_tracks: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced slice [lo, hi) of the track axis owned by `rank` (first ranks get the remainder)."""
     if world < 1 or not (0 <= rank < world):
