@@ -9,7 +9,9 @@ sys.path.insert(0, "/root/reference")
 from transkun.LayersTransformer import ScaledInnerProductIntervalScorer  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-for name, B, P, T, size, seed in [("scorer_B1_P3_T40_D64", 1, 3, 40, 64, 0), ("scorer_B2_P5_T70_D256", 2, 5, 70, 256, 1)]:
+for name, B, P, T, size, seed in [("scorer_B1_P3_T40_D64", 1, 3, 40, 64, 0), ("scorer_B2_P5_T70_D256", 2, 5, 70, 256, 1),
+                                   # an odd number of 32-wide K chunks and a last track group of one (round 2 kernel)
+                                   ("scorer_B1_P9_T130_D96", 1, 9, 130, 96, 2)]:
     torch.manual_seed(seed)
     m = ScaledInnerProductIntervalScorer(size, 1).eval()
     ctx = torch.randn(B, P, T, size)
